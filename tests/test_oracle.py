@@ -1,0 +1,95 @@
+"""CPU: pin the numpy oracle against every golden vector minted from the reference module."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, load_checkpoint
+from oracle import tip_oracle as O
+
+TOL = 5e-5   # fp32 noise floor module-vs-restatement measured in the survey: <= 7.7e-6
+
+
+def _weights(g):
+    if "checkpoint" in g.files:
+        sd = load_checkpoint(str(g["checkpoint"]))
+        if sd is None:
+            pytest.skip("baseline/_ref checkpoint not staged")
+        return sd, dict(with_rnn=True)
+    return (O.random_state_dict(int(g["wseed"]), size_s=int(g["size_s"]),
+                                with_rnn=bool(g["with_rnn"]), with_acc_sum=bool(g["with_acc_sum"])),
+            dict(with_rnn=bool(g["with_rnn"])))
+
+
+FIXTURES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLD, "*.npz"))
+                  if "stream" not in p and "b256" not in p)
+
+
+def test_fixture_inventory():
+    assert len(FIXTURES) >= 14
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_oracle_matches_reference_golden(name):
+    g = np.load(os.path.join(GOLD, name))
+    sd, kw = _weights(g)
+    keep = g["keep_mask"] if "keep_mask" in g.files else None
+    scale = float(g["past_scale"]) if "past_scale" in g.files else 1.0
+    y = O.forward(sd, g["x_imu"], g["x_s"], keep_mask=keep, past_scale=scale, **kw)
+    assert y.shape == g["y"].shape and y.dtype == np.float32
+    assert np.isfinite(y).all()
+    err = np.abs(y - g["y"]).max()
+    assert err < TOL, err
+
+
+def test_oracle_fp64_budget():
+    g = np.load(os.path.join(GOLD, "rw_b3_l39.npz"))
+    sd, kw = _weights(g)
+    y64 = O.forward(sd, g["x_imu"], g["x_s"], dtype=np.float64, **kw)
+    assert np.abs(y64 - g["y"]).max() < TOL
+
+
+def test_oracle_b256_subsample():
+    g = np.load(os.path.join(GOLD, "rw_b256_l40_sub.npz"))
+    sd = O.random_state_dict(int(g["wseed"]))
+    x_imu, x_s = O.synth_inputs(int(g["xseed"]), 256, 40)
+    y = O.forward(sd, x_imu, x_s)
+    assert np.abs(y[g["idx"]] - g["y_sub"]).max() < TOL
+    assert np.abs(y[:, -1] - g["y_last"]).max() < TOL
+    assert abs(y.astype(np.float64).sum() - float(g["y_sum"])) < 1e-2
+
+
+def test_oracle_inputs_not_mutated_and_nan_handled():
+    sd = O.random_state_dict(11)
+    x_imu, x_s = O.synth_inputs(9, 2, 12, nan_frac=0.5)
+    xi0, xs0 = x_imu.copy(), x_s.copy()
+    y = O.forward(sd, x_imu, x_s)
+    assert np.isnan(xs0).any() and np.isfinite(y).all()
+    np.testing.assert_array_equal(x_imu, xi0)
+    np.testing.assert_array_equal(np.isnan(x_s), np.isnan(xs0))
+
+
+def test_oracle_stream_trace():
+    g = np.load(os.path.join(GOLD, "ck_stream200.npz"))
+    sd = load_checkpoint(str(g["checkpoint"]))
+    if sd is None:
+        pytest.skip("baseline/_ref checkpoint not staged")
+    for t in (0, 1, 5, 38, 39, 40, 41, 120, 199):
+        lo = max(0, t + 1 - 40)
+        y = O.forward(sd, g["imu_rows"][lo:t + 1][None], g["s_rows"][lo:t + 1][None])
+        assert np.abs(y[0, -1] - g["y_last"][t]).max() < TOL
+
+
+def test_window_assembler_shapes_and_warmup():
+    rs = np.random.RandomState(0)
+    wa = O.WindowAssembler()
+    outs = []
+    for t in range(60):
+        R = np.linalg.qr(rs.standard_normal((6, 3, 3)))[0].reshape(-1)
+        outs.append(wa.push(np.concatenate((R, rs.standard_normal(18)))))
+    assert all(o is None for o in outs[:5])          # Appendix B: first 5 calls make no model call
+    assert outs[5].shape == (1, 90)
+    assert outs[44].shape == (40, 90) and outs[59].shape == (40, 90)
+    # rows already written are immutable: window t+1 rows[:-1] == window t rows[1:] (IMU part)
+    np.testing.assert_allclose(outs[59][:-1, :72], outs[58][1:, :72], atol=1e-12)
