@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- IMU frames/sec of the TIP hot path on N B200s (replicas only, no per-step collective).
+
+A "step" is one forward of `TF_RNN_Past_State` over one batch of synthetic 6-IMU windows
+(BASELINE.json configs[1]: batch=256, seq_len=40, fp32).  `value` = windows (= output frames)
+per second over all ranks, inputs resident in HBM; `e2e` = the same through the module's public
+call with pinned HOST buffers (H2D + forward + D2H inside the timed region, i.e.
+`model(x_imu.cuda(), x_s.cuda()).cpu()`, real_time_runner_minimal.py:149).
+
+    python bench.py --gpus 1 --steps 50 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...       # the reference's CPU path (oracle port) on host cores
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "transformer-inertial-poser_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "imu_frames_per_sec_seq40_6imu"
+UNIT = "frames/s"
+L_WIN = 40
+CKPT = os.path.join(ROOT, "baseline", "_ref", "model-with-dip9and10.pt")
+
+
+def load_weights():
+    """Released checkpoint when staged (baseline/_ref, copied by build()), else seeded random
+    weights of the same architecture."""
+    from oracle import tip_oracle as O          # weight/input generators only (synthetic data)
+    if os.path.exists(CKPT):
+        sd = {k: v.numpy() for k, v in torch.load(CKPT, map_location="cpu").items()}
+        return sd, "checkpoint model-with-dip9and10.pt"
+    return O.random_state_dict(11), "random-init (seed 11)"
+
+
+def synth(seed, B):
+    from oracle import tip_oracle as O
+    return O.synth_inputs(seed, B, L_WIN)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons DURING the timed region (NVML; nvidia-smi fallback)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.sm_max = index, False, [], set(), None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                if self.nv is not None:
+                    self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    try:
+                        r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, n in names.items():
+                        if r & bit:
+                            self.reasons.add(n)
+                else:
+                    import subprocess
+                    out = subprocess.run(
+                        ["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,"
+                         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                         "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [s.strip() for s in out.strip().split(",")]
+                    self.sm.append(int(f[0]))
+                    self.sm_max = int(f[1])
+                    for v, n in zip(f[2:], ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.005 if self.nv is not None else 0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def build_model(sd, device):
+    from tip_b200 import TF_RNN_Past_State
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = TF_RNN_Past_State(72, 131, rnn_hid_size=512, tf_hid_size=1024, tf_in_dim=256, n_heads=16,
+                              tf_layers=4, dropout=0.0, in_dropout=0.0, past_state_dropout=0.8,
+                              with_acc_sum=True)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    m = m.to(device).eval()
+    m.past_state_dropout = 0.0      # deterministic parity mode
+    return m
+
+
+def cpu_port_rate(sd, B, budget_s, threads, seed=1):
+    """windows/s of the CPU PyTorch port of the reference forward on `threads` host threads."""
+    from oracle import tip_oracle_torch as OT
+    torch.set_num_threads(threads)
+    W = OT.to_torch_state(sd)
+    x_imu, x_s = synth(seed, B)
+    xi, xs = torch.from_numpy(x_imu), torch.from_numpy(x_s)
+    OT.forward(W, xi, xs)                                   # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        OT.forward(W, xi, xs)
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= 64:
+            break
+    return n * B / el, n, el
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the
+    reference .py cannot travel to the GPU box) on all host cores; rank 0 only."""
+    if rank != 0:
+        return
+    sd, wdesc = load_weights()
+    from oracle import tip_oracle_torch as OT
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    W = OT.to_torch_state(sd)
+    # calibrate a bounded per-step sample so (steps+warmup) steps end within ~2 minutes
+    xi, xs = (torch.from_numpy(a) for a in synth(1, 16))
+    OT.forward(W, xi, xs)
+    t0 = time.perf_counter()
+    OT.forward(W, xi, xs)
+    per_win = (time.perf_counter() - t0) / 16
+    Bs = int(max(1, min(args.batch, 120.0 / max(1, args.steps + args.warmup) / per_win)))
+    xi, xs = (torch.from_numpy(a) for a in synth(1, Bs))
+    for _ in range(args.warmup):
+        OT.forward(W, xi, xs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        OT.forward(W, xi, xs)
+    el = time.perf_counter() - t0
+    val = args.steps * Bs / el
+    sample = f"{args.steps} steps x {Bs} windows of the batch={args.batch} L=40 workload (deterministic mode, torch CPU port)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": f"synthetic windows (SURVEY 8d distributions), {wdesc}",
+        "config": {"workload": f"batch={args.batch} synthetic IMU windows, seq_len=40, 6 IMUs, fp32 (BASELINE configs[1])",
+                   "sample_windows_per_step": Bs},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="windows per step per GPU")
+    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05 3xTF32")
+    ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU-baseline work")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+
+    sd, wdesc = load_weights()
+    model = build_model(sd, dev)
+    if world > 1:
+        from tip_b200.replicas import broadcast_weights
+        broadcast_weights(model, src=0)          # the ONE collective: weights at init over NVLink
+    if args.engine:
+        model.set_gemm_engine(args.engine)
+
+    # inputs: several distinct batches, resident in HBM (seed 1 at N=1; 100+rank for replicas)
+    n_sets = 4
+    base_seed = 1 if world == 1 else 100 + rank
+    sets = []
+    for i in range(n_sets):
+        xi, xs = synth(base_seed + 1000 * i, B)
+        sets.append((torch.from_numpy(xi).to(dev), torch.from_numpy(xs).to(dev)))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        model(*sets[i % n_sets])
+    barrier()
+
+    # ---- timed region: K steps, per-step CUDA events on the launch stream, L2 flushed between --
+    model.set_profile(True)
+    model(*sets[0])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_ms, launches = {}, 0
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                                   # evict weights/inputs/activations from L2
+        ev[i][0].record()
+        model(*sets[i % n_sets])
+        ev[i][1].record()
+        launches += model.last_launch_count()
+        if i % 8 == 7 or i == args.steps - 1:           # harvest per-stage events (syncs; outside the event pairs)
+            for name, layer, ms in model.profile():
+                stage_ms.setdefault(name, []).append(ms)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.stop_flag = True
+    sampler.join()
+    model.set_profile(False)
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = world * B * args.steps / (dev_ms / 1e3)
+
+    # ---- e2e: public call with pinned host buffers, H2D + forward + D2H per step ---------------
+    hx = [(torch.from_numpy(synth(base_seed + 7000 + i, B)[0]).pin_memory(),
+           torch.from_numpy(synth(base_seed + 7000 + i, B)[1]).pin_memory()) for i in range(2)]
+    for i in range(3):
+        model(hx[i % 2][0].cuda(non_blocking=True), hx[i % 2][1].cuda(non_blocking=True)).cpu()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        y = model(hx[i % 2][0].to(dev, non_blocking=True), hx[i % 2][1].to(dev, non_blocking=True)).cpu()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * args.steps / float(t.item())
+    h2d = B * L_WIN * (90 + 131) * 4
+    d2h = B * L_WIN * 131 * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per-launch algorithmic flops / CUDA-event duration) --
+    hbm_peak, tf_peak, tf_sus, peak_kind = measured_peaks()
+    M = B * L_WIN
+    stage_flops = {"in_linear": 2.0 * M * 221 * 256, "qkv": 2.0 * M * 256 * 768,
+                   "attention": 2.0 * B * 2 * L_WIN * L_WIN * 256, "out_proj_ln": 2.0 * M * 256 * 256,
+                   "ff1": 2.0 * M * 256 * 1024, "ff2_ln": 2.0 * M * 1024 * 256,
+                   "rnn_ih": 2.0 * M * 256 * 512, "rnn": 2.0 * M * 512 * 512, "head": 2.0 * M * 512 * 131,
+                   "condition": 0.0}
+    per_launch = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    launches_per_fwd = {k: (4 if k in ("qkv", "attention", "out_proj_ln", "ff1", "ff2_ln") else 1) for k in per_launch}
+    totals = {k: per_launch[k] * launches_per_fwd[k] for k in per_launch}
+    dom = max(totals, key=totals.get)
+    tot_stage = sum(totals.values())
+    ach_tf = stage_flops.get(dom, 0.0) / (per_launch[dom] * 1e-3) / 1e12
+    alg_bytes, alg_flops = model.algorithmic_cost(B, L_WIN)
+    fwd_gbs = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    roofline = {
+        "bound": "tensor", "kernel": dom, "achieved": ach_tf, "peak": tf_peak, "unit": "TFLOP/s",
+        "frac": ach_tf / tf_peak, "traffic": None, "peak_kind": f"{peak_kind} bf16 burst (cuBLAS); fp32-parity math is "
+        "3xTF32 so the reachable ceiling is peak/6",
+        "us_per_launch": per_launch[dom] * 1e3, "share_of_step": totals[dom] / tot_stage if tot_stage else None,
+        "stage_us_per_forward": {k: round(v * 1e3, 2) for k, v in sorted(totals.items(), key=lambda kv: -kv[1])},
+        "forward_hbm": {"bound": "hbm", "achieved": fwd_gbs, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": fwd_gbs / hbm_peak, "algorithmic_bytes": alg_bytes},
+        "forward_tensor": {"achieved": alg_flops / (ms_per_step * 1e-3) / 1e12, "peak": tf_peak,
+                           "unit": "TFLOP/s", "frac": alg_flops / (ms_per_step * 1e-3) / 1e12 / tf_peak},
+    }
+    tp = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tp):
+        try:
+            roofline["traffic"] = json.load(open(tp)).get(dom)
+        except Exception:
+            pass
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, n, el = cpu_port_rate(sd, B, args.cpu_budget, threads)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{n} batches of {B} windows (L=40) of the same workload in {el:.1f} s, "
+                                  "CPU PyTorch port of the reference forward (oracle/tip_oracle_torch.py), deterministic mode"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": f"synthetic windows (SURVEY 8d distributions), {wdesc}",
+        "config": {"workload": f"batch={B} synthetic IMU windows per GPU, seq_len=40, 6 IMUs, fp32, tf_layers=4 "
+                               "nhid=1024 heads=16 (BASELINE configs[1]); replicas only",
+                   "l2": "256 MiB memset between timed steps (outside the per-step event pair) + 4 rotating input sets",
+                   "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks",
+                   "engine": {0: "auto", 1: "ffma", 2: "tcgen05-3xtf32"}[args.engine]},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "wall_s_timed_region": t_wall,
+    }
+    if cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

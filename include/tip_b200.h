@@ -1,0 +1,155 @@
+/*
+ * tip_b200.h -- C ABI of the B200-native Transformer-Inertial-Poser hot path.
+ *
+ * The reference has no FFI / plugin boundary: its boundary is the duck-typed
+ * torch.nn.Module `TF_RNN_Past_State` imported by module name
+ *   (/root/reference/offline_testing_simple.py:80, live_demo_new.py:16)
+ * and called once per frame as `model(x_imu.cuda(), x_s.cuda()).cpu()`
+ *   (/root/reference/real_time_runner_minimal.py:149, real_time_runner.py:431).
+ * This header is what a ctypes binding for that call binds instead
+ * (see INTEGRATION.md); the Python mirror of the module lives in
+ * transformer-inertial-poser_b200/simple_transformer_with_state.py.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++ / torch types.
+ *   - `*_dev` pointers are DEVICE pointers (tensor.data_ptr()); `*_host` are host
+ *     pointers.  `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - every call returns a tip_status; tip_last_error(handle) gives the message.
+ *     Nothing throws, exits or synchronises the device unless documented.
+ *   - one handle = one model replica on one GPU (the current device at tip_create).
+ *     Calls on one handle must not overlap (the reference caller is single-threaded).
+ *   - all tensors are fp32, row-major, contiguous.
+ */
+#ifndef TIP_B200_H_
+#define TIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIP_ABI_VERSION 1
+
+typedef enum tip_status {
+    TIP_OK = 0,
+    TIP_ERR_INVALID_ARG = 1,   /* bad shape / null pointer / unsupported hyper-parameter */
+    TIP_ERR_NOT_PACKED = 2,    /* forward before tip_pack_weights */
+    TIP_ERR_CUDA = 3,          /* a CUDA runtime call failed (message has the cudaError string) */
+    TIP_ERR_NO_DEVICE = 4,     /* no sm_100 device available */
+    TIP_ERR_OOM = 5
+} tip_status;
+
+/* Constructor arguments of TF_RNN_Past_State
+ * (/root/reference/simple_transformer_with_state.py:9-17).  The kernels are specialised for the
+ * one architecture the reference ships and constructs (offline_testing_simple.py:87-95,
+ * live_demo_new.py:202-210): tf_in_dim=256, n_heads=16, tf_hid_size=1024, rnn_hid_size=512,
+ * tf_layers<=8; input_size_imu=72, size_s<=160, with_rnn and with_acc_sum free.
+ * Anything else makes tip_create return TIP_ERR_INVALID_ARG. */
+typedef struct tip_dims {
+    int32_t input_size_imu;   /* 72 = 6 IMUs x (9 rotation + 3 acceleration) */
+    int32_t size_s;           /* 131 (5 SBPs) or 119 (2 SBPs) */
+    int32_t rnn_hid_size;     /* 512 */
+    int32_t tf_hid_size;      /* 1024 */
+    int32_t tf_in_dim;        /* 256 */
+    int32_t n_heads;          /* 16 */
+    int32_t tf_layers;        /* 4 */
+    int32_t with_rnn;         /* 1: tanh RNN + Linear(rnn_hid->size_s); 0: Linear(tf_in_dim->size_s) */
+    int32_t with_acc_sum;     /* 1: x_imu carries 18 extra acc-sum columns (90 wide) */
+} tip_dims;
+
+/* Per-call stochastic behaviour of the reference forward (lines :73, :77 and the
+ * nn.TransformerEncoderLayer dropouts).  All-zero = the deterministic parity mode of
+ * SURVEY.md section 8c (eval(), past_state_dropout = 0). */
+typedef struct tip_dropout {
+    float    in_dropout;          /* p on x_imu            (reference :73; 0 in every shipped config) */
+    float    past_state_dropout;  /* p on x_s              (reference :77; ALWAYS live there, 0.8 shipped) */
+    float    encoder_dropout;     /* p inside the encoder  (0.1 when the module is in train(), else 0) */
+    uint64_t seed;                /* counter-based RNG seed for this call (ignored when all p are 0) */
+} tip_dropout;
+
+typedef struct tip_model tip_model;   /* opaque */
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int  tip_abi_version(void);
+/* Mirrors TF_RNN_Past_State.__init__ (:9-54). Binds to the current CUDA device. */
+int  tip_create(const tip_dims* dims, tip_model** out);
+void tip_destroy(tip_model* m);
+const char* tip_last_error(const tip_model* m);   /* m may be NULL: last error of tip_create */
+
+/* ---- weights -------------------------------------------------------------------------------- */
+/* Number of state-dict tensors the model expects: 2 + 12*tf_layers + (with_rnn ? 4 : 0) + 2
+ * (56 for the shipped checkpoints), in the reference's state_dict() order. */
+int  tip_num_weight_tensors(const tip_model* m);
+/* Mirrors load_state_dict + .cuda() (offline_testing_simple.py:96-97): takes DEVICE pointers to
+ * the fp32 tensors in state-dict order, with their element counts (checked against the expected
+ * shapes), and builds the private packed copy (head-permutation folded into in_linear rows,
+ * root-velocity columns zeroed, 1/sqrt(d) folded into W_q/b_q, RNN biases pre-summed, TF32
+ * hi/lo splits).  Asynchronous on `stream`; the source tensors may be freed after the stream
+ * has passed this point. */
+int  tip_pack_weights(tip_model* m, const float* const* tensors_dev, const int64_t* numels,
+                      int n_tensors, void* stream);
+/* Packed weight blob (for the one-off NCCL broadcast of the replica launcher). */
+int  tip_packed_blob(tip_model* m, void** blob_dev, size_t* bytes);
+int  tip_mark_packed(tip_model* m);   /* after the blob was filled by a broadcast */
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* Mirrors TF_RNN_Past_State.forward (:60-102):
+ *   x_imu_dev (B, L, input_size_imu [+18]), x_s_dev (B, L, size_s) -> y_dev (B, L, size_s).
+ * 1 <= L <= 40 (the runner's max_input_l), B >= 1.  Inputs are not modified (reference clones).
+ * keep_mask_dev: optional (B, L, size_s) 0/1 mask; when non-NULL x_s is multiplied by
+ * keep_mask * past_scale INSTEAD of drawing the past_state_dropout mask (deterministic test of :77).
+ * drop may be NULL (= deterministic mode).  Asynchronous on `stream`. */
+int  tip_forward(tip_model* m, const float* x_imu_dev, const float* x_s_dev, float* y_dev,
+                 int B, int L, const float* keep_mask_dev, float past_scale,
+                 const tip_dropout* drop, void* stream);
+
+/* Same call with HOST buffers: H2D of both inputs, forward, D2H of y, and a stream synchronise
+ * -- i.e. exactly `model(x_imu.cuda(), x_s.cuda()).cpu()` (real_time_runner_minimal.py:149).
+ * If last_row_only != 0, y_host is (B, size_s) = y[:, L-1, :] (what :150 consumes). */
+int  tip_forward_host(tip_model* m, const float* x_imu_host, const float* x_s_host, float* y_host,
+                      int B, int L, int last_row_only, const tip_dropout* drop, void* stream);
+
+/* ---- streaming (row a10: the window the runner rebuilds every frame) ------------------------- */
+/* Device-resident sliding windows for `n_streams` independent IMU streams
+ * (replaces real_time_runner_minimal.py:131-147's per-frame re-assembly of the last <=40 rows).
+ * Re-creating resets all streams. */
+int  tip_stream_reset(tip_model* m, int n_streams);
+/* Push one new row per stream (imu_row (S, 72|90), s_row (S, size_s); host or device pointers per
+ * `rows_on_host`), slide each window by one row once it holds 40 (coalesced in-place shift),
+ * run the forward on the current L = min(#rows, 40) and return y[:, L-1, :] as (S, size_s).
+ * With rows_on_host != 0 the call copies in/out and synchronises `stream` before returning. */
+int  tip_stream_step(tip_model* m, const float* imu_row, const float* s_row, float* y_last,
+                     int rows_on_host, const tip_dropout* drop, void* stream);
+int  tip_stream_length(const tip_model* m);   /* current L (0 before the first push) */
+
+/* ---- introspection -------------------------------------------------------------------------- */
+/* Algorithmic bytes / flops of one forward:
+ *   bytes = weight_bytes + B*L*4*(d_in + size_s);  flops = 2*MACs. */
+int  tip_algorithmic_cost(const tip_model* m, int B, int L, double* bytes, double* flops);
+/* Number of kernels the last tip_forward launched (for bench.py's gpu_launches). */
+int  tip_last_launch_count(const tip_model* m);
+/* Select the GEMM engine: 0 = auto (tcgen05 3xTF32 when B*L >= 512, FFMA otherwise),
+ * 1 = force FFMA fp32 kernels, 2 = force tcgen05 3xTF32 kernels. */
+int  tip_set_gemm_engine(tip_model* m, int engine);
+/* CUDA-graph the forward for a fixed (B, L) (used by the streaming path); 0 disables. */
+int  tip_set_use_graphs(tip_model* m, int enable);
+/* Per-stage device timing of the forward (bench.py's roofline leg): when enabled, a CUDA event is
+ * recorded on the launch stream before every kernel of tip_forward.  tip_profile_stages returns
+ * the number of stages the last forward recorded; tip_profile_get synchronises on the events and
+ * returns stage i's name ("in_linear", "qkv", "attention", "out_proj_ln", "ff1", "ff2_ln",
+ * "rnn_ih", "rnn", "head", ...), its layer (-1 if none) and its duration in milliseconds. */
+int  tip_set_profile(tip_model* m, int enable);
+int  tip_profile_stages(const tip_model* m);
+int  tip_profile_get(tip_model* m, int i, char* name, int name_cap, int* layer, float* ms);
+/* Test hook: copy an internal activation buffer of the LAST forward into dst_dev (capacity in
+ * floats; *numel receives the element count): "embed" = encoder output rows (M,256), "qkv" (M,768),
+ * "gi" (M,512), "hs" (M,512); rows are b*L + t.  Asynchronous on `stream`. */
+int  tip_debug_tensor(tip_model* m, const char* name, float* dst_dev, int64_t capacity,
+                      int64_t* numel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIP_B200_H_ */

@@ -1,0 +1,219 @@
+"""GPU: parity of the CUDA hot path (through the C ABI) against the oracle and the golden vectors
+minted from the reference module.  Tolerance (BASELINE.json north_star): 1e-4 max-abs, fp32."""
+import contextlib
+import ctypes as C
+import glob
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD, load_checkpoint
+from oracle import tip_oracle as O
+from tip_b200 import TF_RNN_Past_State, capi
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4          # max-abs, fp32 (north_star); pose block gets the tighter 5e-5 below
+TOL_POSE = 5e-5
+
+
+def make_model(sd, size_s=131, with_rnn=True, with_acc_sum=True, engine=0):
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = TF_RNN_Past_State(72, size_s, rnn_hid_size=512, tf_hid_size=1024, tf_in_dim=256,
+                              n_heads=16, tf_layers=4, dropout=0.0, in_dropout=0.0,
+                              past_state_dropout=0.8, with_rnn=with_rnn, with_acc_sum=with_acc_sum)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    m = m.cuda().eval()
+    m.past_state_dropout = 0.0
+    if engine:
+        m.set_gemm_engine(engine)
+    return m
+
+
+def run(m, x_imu, x_s, **kw):
+    kw = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+    return m(torch.from_numpy(x_imu).cuda(), torch.from_numpy(x_s).cuda(), **kw).cpu().numpy()
+
+
+def _weights(g):
+    if "checkpoint" in g.files:
+        sd = load_checkpoint(str(g["checkpoint"]))
+        if sd is None:
+            pytest.skip("baseline/_ref checkpoint not staged")
+        return sd, {}
+    kw = dict(size_s=int(g["size_s"]), with_rnn=bool(g["with_rnn"]), with_acc_sum=bool(g["with_acc_sum"]))
+    return O.random_state_dict(int(g["wseed"]), **kw), kw
+
+
+FIXTURES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLD, "*.npz"))
+                  if "stream" not in p and "b256" not in p)
+ENGINES = [pytest.param(1, id="ffma"), pytest.param(2, id="tcgen05")]   # tip_set_gemm_engine
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", FIXTURES)
+def test_golden_vectors(name, engine):
+    g = np.load(os.path.join(GOLD, name))
+    sd, kw = _weights(g)
+    m = make_model(sd, engine=engine, **kw)
+    extra = {}
+    if "keep_mask" in g.files:
+        extra = dict(keep_mask=g["keep_mask"], past_scale=float(g["past_scale"]))
+    xi0, xs0 = g["x_imu"].copy(), g["x_s"].copy()
+    y = run(m, g["x_imu"], g["x_s"], **extra)
+    assert y.shape == g["y"].shape and y.dtype == np.float32 and np.isfinite(y).all()
+    err = np.abs(y - g["y"])
+    assert err.max() < TOL, err.max()
+    assert err[..., :108].max() < TOL_POSE, err[..., :108].max()
+    np.testing.assert_array_equal(g["x_imu"], xi0)          # reference clones its inputs (:63-64)
+    np.testing.assert_array_equal(np.isnan(g["x_s"]), np.isnan(xs0))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_b256_full_size(engine):
+    """BASELINE config 2: batch=256, L=40; golden sub-sample + checksums from the reference."""
+    g = np.load(os.path.join(GOLD, "rw_b256_l40_sub.npz"))
+    sd = O.random_state_dict(int(g["wseed"]))
+    x_imu, x_s = O.synth_inputs(int(g["xseed"]), 256, 40)
+    m = make_model(sd, engine=engine)
+    y = run(m, x_imu, x_s)
+    assert np.abs(y[g["idx"]] - g["y_sub"]).max() < TOL
+    assert np.abs(y[:, -1] - g["y_last"]).max() < TOL
+    assert abs(y.astype(np.float64).sum() - float(g["y_sum"])) < 0.5
+    # size-independent properties: batch rows are independent and causal
+    y2 = run(m, x_imu[40:50], x_s[40:50])
+    assert np.abs(y2 - y[40:50]).max() < 2e-5
+    y3 = run(m, x_imu[:8, :17], x_s[:8, :17])               # causal mask: a prefix gives the prefix
+    assert np.abs(y3 - y[:8, :17]).max() < 2e-5
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_oracle_parity_random_shapes(engine):
+    sd = O.random_state_dict(21)
+    m = make_model(sd, engine=engine)
+    for seed, (B, L) in enumerate([(1, 1), (2, 2), (7, 13), (33, 40), (130, 9), (1, 39), (600, 3)]):
+        x_imu, x_s = O.synth_inputs(100 + seed, B, L, nan_frac=0.2)
+        y = run(m, x_imu, x_s)
+        ref = O.forward(sd, x_imu, x_s)
+        assert np.abs(y - ref).max() < TOL, (B, L, np.abs(y - ref).max())
+
+
+def test_large_batch_chunking():
+    """B larger than one workspace pass (CHUNK_WINDOWS=1024) equals the per-chunk results."""
+    sd = O.random_state_dict(22)
+    m = make_model(sd)
+    x_imu, x_s = O.synth_inputs(7, 1100, 6)
+    y = run(m, x_imu, x_s)
+    ref = O.forward(sd, x_imu[1000:], x_s[1000:])
+    assert np.abs(y[1000:] - ref).max() < TOL
+
+
+def test_stream_trace_matches_reference():
+    """200-frame closed-loop trace minted from the reference: L ramps 1..40 then slides."""
+    g = np.load(os.path.join(GOLD, "ck_stream200.npz"))
+    sd = load_checkpoint(str(g["checkpoint"]))
+    if sd is None:
+        pytest.skip("baseline/_ref checkpoint not staged")
+    m = make_model(sd)
+    from tip_b200.streaming import StreamSession
+    for on_host in (True, False):
+        s = StreamSession(m, n_streams=1)
+        worst = 0.0
+        for t in range(200):
+            if on_host:
+                y = s.step(g["imu_rows"][t][None], g["s_rows"][t][None])
+            else:
+                y = s.step(torch.from_numpy(g["imu_rows"][t][None]).cuda(),
+                           torch.from_numpy(g["s_rows"][t][None]).cuda()).cpu().numpy()
+            worst = max(worst, float(np.abs(y[0] - g["y_last"][t]).max()))
+        assert s.length == 40
+        assert worst < TOL, worst
+
+
+def test_multi_stream_session_matches_windows():
+    sd = O.random_state_dict(23)
+    m = make_model(sd)
+    from tip_b200.streaming import StreamSession
+    S, T = 5, 55
+    x_imu, x_s = O.synth_inputs(31, S, T, nan_frac=0.1)
+    s = StreamSession(m, n_streams=S)
+    for t in range(T):
+        y = s.step(x_imu[:, t], x_s[:, t])
+        if t in (0, 3, 39, 40, 54):
+            lo = max(0, t + 1 - 40)
+            ref = O.forward(sd, x_imu[:, lo:t + 1], x_s[:, lo:t + 1])[:, -1]
+            assert np.abs(y - ref).max() < TOL, t
+
+
+def test_forward_host_entry():
+    sd = O.random_state_dict(24)
+    m = make_model(sd)
+    x_imu, x_s = O.synth_inputs(41, 3, 40)
+    ref = O.forward(sd, x_imu, x_s)
+    y = m.forward_host(x_imu, x_s).numpy()
+    assert np.abs(y - ref).max() < TOL
+    yl = m.forward_host(x_imu, x_s, last_row_only=True).numpy()
+    assert yl.shape == (3, 131) and np.abs(yl - ref[:, -1]).max() < TOL
+
+
+def test_repack_on_load_state_dict_and_param_update():
+    sd_a, sd_b = O.random_state_dict(25), O.random_state_dict(26)
+    m = make_model(sd_a)
+    x_imu, x_s = O.synth_inputs(42, 2, 40)
+    ya = run(m, x_imu, x_s)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd_b.items()})
+    yb = run(m, x_imu, x_s)
+    assert np.abs(ya - O.forward(sd_a, x_imu, x_s)).max() < TOL
+    assert np.abs(yb - O.forward(sd_b, x_imu, x_s)).max() < TOL
+    with torch.no_grad():
+        m.linear.bias.add_(1.0)
+    yc = run(m, x_imu, x_s)
+    assert np.abs(yc - (yb + 1.0)).max() < 1e-5
+
+
+def test_error_behaviour():
+    sd = O.random_state_dict(27)
+    m = make_model(sd)
+    x_imu, x_s = O.synth_inputs(43, 1, 40)
+    xi, xs = torch.from_numpy(x_imu).cuda(), torch.from_numpy(x_s).cuda()
+    with pytest.raises(RuntimeError):
+        m(torch.cat([xi, xi], 1), torch.cat([xs, xs], 1))           # L = 80 > 40
+    with pytest.raises(RuntimeError):
+        m(xi[:, :, :72], xs)                                         # wrong width
+    lib = capi.load_library()
+    h = C.c_void_p()
+    d = capi.TipDims(72, 131, 512, 1024, 256, 16, 4, 1, 1)
+    assert lib.tip_create(C.byref(d), C.byref(h)) == 0
+    y = torch.empty(1, 40, 131, device="cuda")
+    rc = lib.tip_forward(h, xi.data_ptr(), xs.data_ptr(), y.data_ptr(), 1, 40, None, 1.0, None, None)
+    assert rc == 2 and b"pack" in lib.tip_last_error(h)              # TIP_ERR_NOT_PACKED
+    lib.tip_destroy(h)
+
+
+def test_stochastic_mode_statistics():
+    """As-shipped behaviour: past-state dropout p=0.8 live on every call, encoder dropout in
+    train().  Not bit-equal to torch's Philox stream; check determinism per seed, variability
+    across seeds and that the mean over masks of the embed stage matches the mask-free value
+    (dropout is unbiased and in_linear is linear in x_s)."""
+    sd = O.random_state_dict(28)
+    m = make_model(sd)
+    m.past_state_dropout = 0.8
+    x_imu, x_s = O.synth_inputs(44, 64, 40, nan_frac=0.0)
+    xi, xs = torch.from_numpy(x_imu).cuda(), torch.from_numpy(x_s).cuda()
+    torch.manual_seed(5)
+    y1 = m(xi, xs).cpu()
+    torch.manual_seed(5)
+    y2 = m(xi, xs).cpu()
+    y3 = m(xi, xs).cpu()
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    assert torch.isfinite(y1).all()
+    m.past_state_dropout = 0.0
+    y0 = m(xi, xs).cpu()
+    assert (y1 - y0).abs().max() > 1e-2
+    m.train()                      # encoder dropouts live
+    y4, y5 = m(xi, xs).cpu(), m(xi, xs).cpu()
+    assert not torch.equal(y4, y5) and torch.isfinite(y4).all()
+    m.eval()
+    assert torch.equal(m(xi, xs).cpu(), y0)

@@ -93,3 +93,14 @@ def test_window_assembler_shapes_and_warmup():
     assert outs[44].shape == (40, 90) and outs[59].shape == (40, 90)
     # rows already written are immutable: window t+1 rows[:-1] == window t rows[1:] (IMU part)
     np.testing.assert_allclose(outs[59][:-1, :72], outs[58][1:, :72], atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["rw_b3_l39.npz", "rw_b2_l33_nornn.npz", "rw_b5_l40_s119.npz",
+                                  "ck_model-with-dip9and10_b1_l40.npz"])
+def test_torch_port_matches_reference_golden(name):
+    """The CPU PyTorch port timed by bench.py's reference arm is pinned by the same goldens."""
+    from oracle import tip_oracle_torch as OT
+    g = np.load(os.path.join(GOLD, name))
+    sd, kw = _weights(g)
+    y = OT.forward(OT.to_torch_state(sd), g["x_imu"], g["x_s"], **kw).numpy()
+    assert np.abs(y - g["y"]).max() < TOL

@@ -1,0 +1,668 @@
+// C ABI of the TIP hot path (include/tip_b200.h): handle, weight packing, forward orchestration,
+// host-buffer entry point and the streaming window path.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "tip_common.cuh"
+#include "tip_simt.cuh"
+#include "tip_umma.cuh"
+
+using namespace tip;
+
+namespace {
+std::string g_create_error;
+constexpr int CHUNK_WINDOWS = 1024;   // windows per pass through the workspace
+}  // namespace
+
+struct tip_model {
+    tip_dims cdims{};
+    Dims d{};
+    PackOff off{};
+    int device = 0;
+    float* blob = nullptr;
+    bool packed = false;
+    int engine = 0;           // 0 auto, 1 FFMA, 2 tcgen05
+    int use_graphs = 1;
+    int launches = 0;
+    int64_t last_rows = 0;
+    std::string err;
+
+    // workspace (capacity in rows)
+    int cap_rows = 0;
+    float* ws = nullptr;
+    float *xin = nullptr, *xa = nullptr, *xb = nullptr, *qkv = nullptr, *att = nullptr,
+          *hid = nullptr, *gi = nullptr, *hs = nullptr;
+    size_t plane_xin = 0, plane_e = 0, plane_f = 0, plane_r = 0;   // hi->lo plane strides (floats)
+    UmmaMaps maps;            // TMA descriptors of the workspace + weights (tcgen05 engine)
+    bool maps_ready = false;
+
+    // host-entry staging
+    size_t host_cap = 0;      // windows*L capacity in rows
+    float *h_in = nullptr, *h_out = nullptr, *d_ximu = nullptr, *d_xs = nullptr, *d_y = nullptr;
+
+    // streaming state
+    int n_streams = 0, stream_len = 0;
+    float *win_imu = nullptr, *win_s = nullptr, *st_rows = nullptr, *st_ximu = nullptr,
+          *st_xs = nullptr, *st_y = nullptr, *st_ylast = nullptr, *h_rows = nullptr, *h_ylast = nullptr;
+    cudaGraphExec_t st_graph = nullptr;   // captured steady-state step (L == MAXL)
+    int st_graph_launches = 0;
+
+    // per-stage profiling (tip_set_profile)
+    int profile = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::string> st_names;
+    std::vector<int> st_layers;
+
+    void set_error(const std::string& s) { err = s; }
+};
+
+// record "a stage named `name` starts here" (name == nullptr: end of the forward)
+static void mark(tip_model* m, cudaStream_t st, const char* name, int layer = -1) {
+    if (!m->profile) return;
+    const size_t ev_i = m->st_names.size();   // event i opens stage i and closes stage i-1
+    while (m->ev_pool.size() <= ev_i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        m->ev_pool.push_back(e);
+    }
+    cudaEventRecord(m->ev_pool[ev_i], st);
+    if (name) { m->st_names.push_back(name); m->st_layers.push_back(layer); }
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static void compute_offsets(tip_model* m) {
+    const Dims& d = m->d;
+    PackOff& o = m->off;
+    size_t p = 0;
+    auto take = [&](size_t n) { size_t r = p; p = align_up(p + n, 64); return r; };   // 256-byte aligned
+    o.win = take((size_t)E * d.kin_pad);
+    o.bin = take(E);
+    o.win_hi = take((size_t)E * d.kin_pad);
+    o.win_lo = take((size_t)E * d.kin_pad);
+    for (int l = 0; l < d.layers; ++l) {
+        LayerOff& L = o.layer[l];
+        L.wqkv = take((size_t)3 * E * E); L.bqkv = take(3 * E);
+        L.wo = take((size_t)E * E);       L.bo = take(E);
+        L.w1 = take((size_t)F * E);       L.b1 = take(F);
+        L.w2 = take((size_t)E * F);       L.b2 = take(E);
+        L.g1 = take(E); L.be1 = take(E); L.g2 = take(E); L.be2 = take(E);
+        L.wqkv_hi = take((size_t)3 * E * E); L.wqkv_lo = take((size_t)3 * E * E);
+        L.wo_hi = take((size_t)E * E);       L.wo_lo = take((size_t)E * E);
+        L.w1_hi = take((size_t)F * E);       L.w1_lo = take((size_t)F * E);
+        L.w2_hi = take((size_t)E * F);       L.w2_lo = take((size_t)E * F);
+    }
+    if (d.with_rnn) {
+        o.wih = take((size_t)R * E); o.brnn = take(R);
+        o.whh = take((size_t)R * R); o.whh_t = take((size_t)R * R);
+        o.wih_hi = take((size_t)R * E); o.wih_lo = take((size_t)R * E);
+    }
+    o.wl = take((size_t)HEAD_NPAD * d.khead); o.bl = take(HEAD_NPAD);
+    o.wl_hi = take((size_t)HEAD_NPAD * d.khead); o.wl_lo = take((size_t)HEAD_NPAD * d.khead);
+    o.total = p;
+}
+
+extern "C" int tip_abi_version(void) { return TIP_ABI_VERSION; }
+
+extern "C" const char* tip_last_error(const tip_model* m) {
+    return m ? m->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int tip_create(const tip_dims* dims, tip_model** out) {
+    if (!dims || !out) { g_create_error = "null argument"; return TIP_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (dims->tf_in_dim != E || dims->n_heads != NH || dims->tf_hid_size != F ||
+        dims->rnn_hid_size != R || dims->tf_layers < 1 || dims->tf_layers > MAX_LAYERS ||
+        dims->input_size_imu != 72 || dims->size_s < 111 || dims->size_s > HEAD_NPAD) {
+        g_create_error =
+            "unsupported hyper-parameters: kernels are specialised for tf_in_dim=256, n_heads=16, "
+            "tf_hid_size=1024, rnn_hid_size=512, input_size_imu=72, 111<=size_s<=144, tf_layers<=8";
+        return TIP_ERR_INVALID_ARG;
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { g_create_error = "no CUDA device"; return TIP_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        g_create_error = "tip_b200 kernels are built for sm_100a only (device is not compute 10.x)";
+        return TIP_ERR_NO_DEVICE;
+    }
+    tip_model* m = new tip_model();
+    m->cdims = *dims;
+    m->device = dev;
+    m->d.n_imu = dims->input_size_imu + (dims->with_acc_sum ? 18 : 0);
+    m->d.size_s = dims->size_s;
+    m->d.d_in = m->d.n_imu + dims->size_s;
+    m->d.kin_pad = (int)align_up(m->d.d_in, 32);
+    m->d.layers = dims->tf_layers;
+    m->d.with_rnn = dims->with_rnn ? 1 : 0;
+    m->d.khead = dims->with_rnn ? R : E;
+    compute_offsets(m);
+    cudaError_t e = cudaMalloc(&m->blob, m->off.total * sizeof(float));
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaMalloc(weights): ") + cudaGetErrorString(e);
+        delete m;
+        return TIP_ERR_OOM;
+    }
+    cudaMemset(m->blob, 0, m->off.total * sizeof(float));
+    *out = m;
+    return TIP_OK;
+}
+
+static void free_stream_state(tip_model* m) {
+    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    for (float** p : {&m->win_imu, &m->win_s, &m->st_rows, &m->st_ximu, &m->st_xs, &m->st_y, &m->st_ylast})
+        if (*p) { cudaFree(*p); *p = nullptr; }
+    for (float** p : {&m->h_rows, &m->h_ylast})
+        if (*p) { cudaFreeHost(*p); *p = nullptr; }
+    m->n_streams = 0;
+    m->stream_len = 0;
+}
+
+extern "C" void tip_destroy(tip_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    free_stream_state(m);
+    for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
+    if (m->blob) cudaFree(m->blob);
+    if (m->ws) cudaFree(m->ws);
+    for (float* p : {m->d_ximu, m->d_xs, m->d_y}) if (p) cudaFree(p);
+    for (float* p : {m->h_in, m->h_out}) if (p) cudaFreeHost(p);
+    delete m;
+}
+
+extern "C" int tip_num_weight_tensors(const tip_model* m) {
+    return m ? 2 + 12 * m->d.layers + (m->d.with_rnn ? 4 : 0) + 2 : 0;
+}
+
+extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64_t* numels, int n,
+                                void* stream_) {
+    if (!m || !t || !numels) return TIP_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream_;
+    const Dims& d = m->d;
+    if (n != tip_num_weight_tensors(m)) { m->set_error("wrong number of weight tensors"); return TIP_ERR_INVALID_ARG; }
+    // expected element counts in state-dict order
+    std::vector<int64_t> exp;
+    exp.push_back((int64_t)E * d.d_in); exp.push_back(E);
+    for (int l = 0; l < d.layers; ++l)
+        for (int64_t v : {(int64_t)3 * E * E, (int64_t)3 * E, (int64_t)E * E, (int64_t)E, (int64_t)F * E,
+                          (int64_t)F, (int64_t)E * F, (int64_t)E, (int64_t)E, (int64_t)E, (int64_t)E, (int64_t)E})
+            exp.push_back(v);
+    if (d.with_rnn) { exp.push_back((int64_t)R * E); exp.push_back((int64_t)R * R); exp.push_back(R); exp.push_back(R); }
+    exp.push_back((int64_t)d.size_s * d.khead); exp.push_back(d.size_s);
+    for (int i = 0; i < n; ++i)
+        if (numels[i] != exp[i] || t[i] == nullptr) {
+            m->set_error("weight tensor " + std::to_string(i) + " has " + std::to_string(numels[i]) +
+                         " elements, expected " + std::to_string(exp[i]));
+            return TIP_ERR_INVALID_ARG;
+        }
+    TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    float* B = m->blob;
+    const PackOff& o = m->off;
+    auto copy = [&](size_t dst, const float* src, size_t cnt) {
+        return cudaMemcpyAsync(B + dst, src, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    };
+    auto split = [&](size_t src, size_t hi, size_t lo, size_t cnt) {
+        pack_split_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(B + src, B + hi, B + lo, (int64_t)cnt);
+    };
+    int i = 0;
+    pack_in_linear_kernel<<<(E * d.kin_pad + 255) / 256, 256, 0, st>>>(t[0], t[1], B + o.win, B + o.bin,
+                                                                     d.d_in, d.kin_pad, d.n_imu);
+    split(o.win, o.win_hi, o.win_lo, (size_t)E * d.kin_pad);
+    i = 2;
+    for (int l = 0; l < d.layers; ++l) {
+        const LayerOff& L = o.layer[l];
+        // 1/sqrt(head_dim) = 0.25 folded into the q rows (exact: power of two)
+        pack_scale_rows_kernel<<<(3 * E * E + 255) / 256, 256, 0, st>>>(t[i], B + L.wqkv, (int64_t)3 * E * E,
+                                                                       (int64_t)E * E, 0.25f);
+        pack_scale_rows_kernel<<<(3 * E + 255) / 256, 256, 0, st>>>(t[i + 1], B + L.bqkv, 3 * E, E, 0.25f);
+        TIP_CUDA_TRY(m, copy(L.wo, t[i + 2], (size_t)E * E));
+        TIP_CUDA_TRY(m, copy(L.bo, t[i + 3], E));
+        TIP_CUDA_TRY(m, copy(L.w1, t[i + 4], (size_t)F * E));
+        TIP_CUDA_TRY(m, copy(L.b1, t[i + 5], F));
+        TIP_CUDA_TRY(m, copy(L.w2, t[i + 6], (size_t)E * F));
+        TIP_CUDA_TRY(m, copy(L.b2, t[i + 7], E));
+        TIP_CUDA_TRY(m, copy(L.g1, t[i + 8], E));
+        TIP_CUDA_TRY(m, copy(L.be1, t[i + 9], E));
+        TIP_CUDA_TRY(m, copy(L.g2, t[i + 10], E));
+        TIP_CUDA_TRY(m, copy(L.be2, t[i + 11], E));
+        split(L.wqkv, L.wqkv_hi, L.wqkv_lo, (size_t)3 * E * E);
+        split(L.wo, L.wo_hi, L.wo_lo, (size_t)E * E);
+        split(L.w1, L.w1_hi, L.w1_lo, (size_t)F * E);
+        split(L.w2, L.w2_hi, L.w2_lo, (size_t)E * F);
+        i += 12;
+    }
+    if (d.with_rnn) {
+        TIP_CUDA_TRY(m, copy(o.wih, t[i], (size_t)R * E));
+        TIP_CUDA_TRY(m, copy(o.whh, t[i + 1], (size_t)R * R));
+        pack_transpose_kernel<<<dim3(R / 32, R / 32), dim3(32, 32), 0, st>>>(t[i + 1], B + o.whh_t, R);
+        pack_add_kernel<<<(R + 255) / 256, 256, 0, st>>>(t[i + 2], t[i + 3], B + o.brnn, R);
+        split(o.wih, o.wih_hi, o.wih_lo, (size_t)R * E);
+        i += 4;
+    }
+    pack_pad_rows_kernel<<<(HEAD_NPAD * d.khead + 255) / 256, 256, 0, st>>>(t[i], B + o.wl, d.size_s, HEAD_NPAD, d.khead);
+    pack_pad_rows_kernel<<<1, 256, 0, st>>>(t[i + 1], B + o.bl, d.size_s, HEAD_NPAD, 1);
+    split(o.wl, o.wl_hi, o.wl_lo, (size_t)HEAD_NPAD * d.khead);
+    TIP_CUDA_TRY(m, cudaGetLastError());
+    m->packed = true;
+    m->maps_ready = false;
+    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    return TIP_OK;
+}
+
+extern "C" int tip_packed_blob(tip_model* m, void** blob, size_t* bytes) {
+    if (!m || !blob || !bytes) return TIP_ERR_INVALID_ARG;
+    *blob = m->blob;
+    *bytes = m->off.total * sizeof(float);
+    return TIP_OK;
+}
+extern "C" int tip_mark_packed(tip_model* m) {
+    if (!m) return TIP_ERR_INVALID_ARG;
+    m->packed = true;
+    m->maps_ready = false;
+    return TIP_OK;
+}
+extern "C" int tip_set_gemm_engine(tip_model* m, int engine) {
+    if (!m || engine < 0 || engine > 2) return TIP_ERR_INVALID_ARG;
+    m->engine = engine;
+    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    return TIP_OK;
+}
+extern "C" int tip_set_use_graphs(tip_model* m, int enable) {
+    if (!m) return TIP_ERR_INVALID_ARG;
+    m->use_graphs = enable ? 1 : 0;
+    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    return TIP_OK;
+}
+extern "C" int tip_last_launch_count(const tip_model* m) { return m ? m->launches : 0; }
+
+extern "C" int tip_set_profile(tip_model* m, int enable) {
+    if (!m) return TIP_ERR_INVALID_ARG;
+    m->profile = enable ? 1 : 0;
+    m->st_names.clear();
+    m->st_layers.clear();
+    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    return TIP_OK;
+}
+extern "C" int tip_profile_stages(const tip_model* m) { return m ? (int)m->st_names.size() : 0; }
+extern "C" int tip_profile_get(tip_model* m, int i, char* name, int name_cap, int* layer, float* ms) {
+    if (!m || i < 0 || i >= (int)m->st_names.size() || (size_t)i + 1 >= m->ev_pool.size()) return TIP_ERR_INVALID_ARG;
+    if (name && name_cap > 0) { strncpy(name, m->st_names[i].c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (layer) *layer = m->st_layers[i];
+    if (ms) {
+        TIP_CUDA_TRY(m, cudaEventSynchronize(m->ev_pool[i + 1]));
+        TIP_CUDA_TRY(m, cudaEventElapsedTime(ms, m->ev_pool[i], m->ev_pool[i + 1]));
+    }
+    return TIP_OK;
+}
+
+extern "C" int tip_debug_tensor(tip_model* m, const char* name, float* dst, int64_t capacity,
+                                int64_t* numel, void* stream_) {
+    if (!m || !name || !numel) return TIP_ERR_INVALID_ARG;
+    const std::string n(name);
+    const int64_t rows = m->last_rows;
+    const float* src = nullptr;
+    if (n == "embed")    { src = m->xa;  *numel = rows * E; }
+    else if (n == "qkv") { src = m->qkv; *numel = rows * 3 * E; }
+    else if (n == "gi")  { src = m->gi;  *numel = rows * R; }
+    else if (n == "hs")  { src = m->hs;  *numel = rows * R; }
+    else { m->set_error("tip_debug_tensor: unknown buffer " + n); return TIP_ERR_INVALID_ARG; }
+    if (dst) {
+        if (capacity < *numel || !src) { m->set_error("tip_debug_tensor: capacity too small"); return TIP_ERR_INVALID_ARG; }
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(dst, src, *numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+    }
+    return TIP_OK;
+}
+
+extern "C" int tip_algorithmic_cost(const tip_model* m, int B, int L, double* bytes, double* flops) {
+    if (!m || B < 1 || L < 1) return TIP_ERR_INVALID_ARG;
+    const Dims& d = m->d;
+    double wparams = (double)E * d.d_in + E;
+    wparams += d.layers * ((double)3 * E * E + 3 * E + (double)E * E + E + (double)F * E + F + (double)E * F + E + 4.0 * E);
+    if (d.with_rnn) wparams += (double)R * E + (double)R * R + 2.0 * R;
+    wparams += (double)d.size_s * d.khead + d.size_s;
+    double macs_row = (double)E * d.d_in + d.layers * ((double)3 * E * E + (double)E * E + 2.0 * E * F) +
+                      (d.with_rnn ? (double)R * E + (double)R * R : 0.0) + (double)d.size_s * d.khead;
+    double macs_attn = d.layers * 2.0 * (double)L * L * E;   // QK^T + PV, dense (unmasked) count
+    if (bytes) *bytes = wparams * 4.0 + (double)B * L * 4.0 * (d.d_in + d.size_s);
+    if (flops) *flops = 2.0 * B * (macs_row * L + macs_attn);
+    return TIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int ensure_workspace(tip_model* m, int rows) {
+    if (rows <= m->cap_rows) return TIP_OK;
+    const Dims& d = m->d;
+    int cap = (int)align_up((size_t)std::max(rows, 128), 128);
+    if (m->ws) { cudaFree(m->ws); m->ws = nullptr; m->cap_rows = 0; }
+    m->plane_xin = (size_t)cap * d.kin_pad;
+    m->plane_e = (size_t)cap * E;
+    m->plane_f = (size_t)cap * F;
+    m->plane_r = (size_t)cap * R;
+    size_t p = 0;
+    auto take = [&](size_t n) { size_t r = p; p = align_up(p + n, 256); return r; };
+    const size_t o_xin = take(2 * m->plane_xin), o_xa = take(2 * m->plane_e), o_xb = take(2 * m->plane_e),
+                 o_qkv = take((size_t)cap * 3 * E), o_att = take(2 * m->plane_e),
+                 o_hid = take(2 * m->plane_f), o_gi = take(m->plane_r), o_hs = take(2 * m->plane_r);
+    cudaError_t e = cudaMalloc(&m->ws, p * sizeof(float));
+    if (e != cudaSuccess) {
+        m->set_error(std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e));
+        return TIP_ERR_OOM;
+    }
+    cudaMemset(m->ws, 0, p * sizeof(float));
+    m->xin = m->ws + o_xin; m->xa = m->ws + o_xa; m->xb = m->ws + o_xb; m->qkv = m->ws + o_qkv;
+    m->att = m->ws + o_att; m->hid = m->ws + o_hid; m->gi = m->ws + o_gi; m->hs = m->ws + o_hs;
+    m->cap_rows = cap;
+    m->maps_ready = false;
+    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    return TIP_OK;
+}
+
+static void launch_sgemm(tip_model* m, cudaStream_t st, const float* A, int lda, const float* W, int ldw,
+                         int M, int N, int K, const Epi& ep, bool ln) {
+    if (ln) {
+        sgemm_nt_kernel<32, 256, 4, true><<<dim3(1, (M + 31) / 32), 256, 0, st>>>(A, lda, W, ldw, M, N, K, ep);
+    } else if (M >= 1024) {
+        sgemm_nt_kernel<128, 128, 8, false><<<dim3((N + 127) / 128, (M + 127) / 128), 256, 0, st>>>(A, lda, W, ldw, M, N, K, ep);
+    } else {
+        sgemm_nt_kernel<32, 256, 4, false><<<dim3((N + 255) / 256, (M + 31) / 32), 256, 0, st>>>(A, lda, W, ldw, M, N, K, ep);
+    }
+    m->launches++;
+}
+
+static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, float* out, float* out_lo,
+                             int B, int L, float drop_p, uint64_t seed) {
+    if (B >= 64) attention_kernel<1, 8><<<dim3(B, NH / 8), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
+    else         attention_kernel<4, 2><<<dim3(B, NH / 2), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
+    m->launches++;
+}
+
+static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs, float* hs_lo, int B, int L) {
+    const float* whh_t = m->blob + m->off.whh_t;
+    if (B >= 8 * 64) rnn_stream_kernel<8><<<(B + 7) / 8, R, 0, st>>>(gi, whh_t, hs, hs_lo, B, L);
+    else if (B >= 2 * 74) rnn_stream_kernel<2><<<(B + 1) / 2, R, 0, st>>>(gi, whh_t, hs, hs_lo, B, L);
+    else rnn_stream_kernel<1><<<B, R, 0, st>>>(gi, whh_t, hs, hs_lo, B, L);
+    m->launches++;
+}
+
+// One pass over <= CHUNK_WINDOWS windows.
+static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, float* y, int B, int L,
+                         const float* keep_mask, float past_scale, const tip_dropout* drop,
+                         cudaStream_t st) {
+    const Dims& d = m->d;
+    const PackOff& o = m->off;
+    const float* W = m->blob;
+    const int M = B * L;
+    m->last_rows = M;
+    int rc = ensure_workspace(m, M);
+    if (rc != TIP_OK) return rc;
+    const float p_in = drop ? drop->in_dropout : 0.f;
+    const float p_past = drop ? drop->past_state_dropout : 0.f;
+    const float p_enc = drop ? drop->encoder_dropout : 0.f;
+    const uint64_t seed = drop ? drop->seed : 0;
+    const bool umma = (m->engine == 2) || (m->engine == 0 && UMMA_AVAILABLE && M >= 512);
+    if (umma) {
+        if (!m->maps_ready) {
+            rc = umma_build_maps(m->maps, m->blob, o, d, m->xin, m->plane_xin, m->xa, m->xb, m->att,
+                                 m->plane_e, m->hid, m->plane_f, m->hs, m->plane_r, m->cap_rows, m->err);
+            if (rc != TIP_OK) return rc;
+            m->maps_ready = true;
+        }
+    }
+    float* lo_xin = umma ? m->xin + m->plane_xin : nullptr;
+    float* lo_xa = umma ? m->xa + m->plane_e : nullptr;
+    float* lo_xb = umma ? m->xb + m->plane_e : nullptr;
+    float* lo_att = umma ? m->att + m->plane_e : nullptr;
+    float* lo_hid = umma ? m->hid + m->plane_f : nullptr;
+    float* lo_hs = umma ? m->hs + m->plane_r : nullptr;
+
+    m->st_names.clear();
+    m->st_layers.clear();
+    mark(m, st, "condition");
+    {
+        const int64_t total = (int64_t)M * d.kin_pad;
+        const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+        condition_kernel<<<blocks, 256, 0, st>>>(x_imu, x_s, keep_mask, past_scale, m->xin, lo_xin, M, d.n_imu,
+                                                 d.size_s, d.kin_pad, p_in, p_past, seed);
+        m->launches++;
+    }
+    auto gemm = [&](int which, int layer, const float* A, int K, const float* Wp, int N, Epi ep, bool ln) {
+        if (umma) {
+            umma_gemm(m->maps, which, layer, M, N, K, ep, ln, st);
+            m->launches++;
+        } else {
+            launch_sgemm(m, st, A, K, Wp, K, M, N, K, ep, ln);
+        }
+    };
+    Epi ep{};
+    // in_linear (+ folded head permutation)                                      reference :79-89
+    mark(m, st, "in_linear");
+    ep = Epi{}; ep.bias = W + o.bin; ep.out = m->xa; ep.out_lo = lo_xa; ep.ldc = E;
+    gemm(UG_IN, 0, m->xin, d.kin_pad, W + o.win, E, ep, false);
+    for (int l = 0; l < d.layers; ++l) {                                        // reference :91
+        const LayerOff& Lo = o.layer[l];
+        mark(m, st, "qkv", l);
+        ep = Epi{}; ep.bias = W + Lo.bqkv; ep.out = m->qkv; ep.ldc = 3 * E;
+        gemm(UG_QKV, l, m->xa, E, W + Lo.wqkv, 3 * E, ep, false);
+        mark(m, st, "attention", l);
+        launch_attention(m, st, m->qkv, m->att, lo_att, B, L, p_enc, seed + 101 * (l + 1));
+        mark(m, st, "out_proj_ln", l);
+        ep = Epi{}; ep.bias = W + Lo.bo; ep.resid = m->xa; ep.resid_lo = lo_xa; ep.ldr = E;
+        ep.gamma = W + Lo.g1; ep.beta = W + Lo.be1; ep.out = m->xb; ep.out_lo = lo_xb; ep.ldc = E;
+        ep.drop_p = p_enc; ep.seed = seed + 211 * (l + 1);
+        gemm(UG_OUT, l, m->att, E, W + Lo.wo, E, ep, true);
+        mark(m, st, "ff1", l);
+        ep = Epi{}; ep.bias = W + Lo.b1; ep.relu = 1; ep.out = m->hid; ep.out_lo = lo_hid; ep.ldc = F;
+        ep.drop_p = p_enc; ep.seed = seed + 307 * (l + 1);
+        gemm(UG_FF1, l, m->xb, E, W + Lo.w1, F, ep, false);
+        mark(m, st, "ff2_ln", l);
+        ep = Epi{}; ep.bias = W + Lo.b2; ep.resid = m->xb; ep.resid_lo = lo_xb; ep.ldr = E;
+        ep.gamma = W + Lo.g2; ep.beta = W + Lo.be2; ep.out = m->xa; ep.out_lo = lo_xa; ep.ldc = E;
+        ep.drop_p = p_enc; ep.seed = seed + 401 * (l + 1);
+        gemm(UG_FF2, l, m->hid, F, W + Lo.w2, E, ep, true);
+    }
+    if (d.with_rnn) {                                                           // reference :95-99
+        mark(m, st, "rnn_ih");
+        ep = Epi{}; ep.bias = W + o.brnn; ep.out = m->gi; ep.ldc = R;
+        gemm(UG_IH, 0, m->xa, E, W + o.wih, R, ep, false);
+        mark(m, st, "rnn");
+        launch_rnn(m, st, m->gi, m->hs, lo_hs, B, L);
+        mark(m, st, "head");
+        ep = Epi{}; ep.bias = W + o.bl; ep.out = y; ep.ldc = d.size_s;
+        gemm(UG_HEAD_R, 0, m->hs, R, W + o.wl, d.size_s, ep, false);            // reference :102
+    } else {
+        mark(m, st, "head");
+        ep = Epi{}; ep.bias = W + o.bl; ep.out = y; ep.ldc = d.size_s;
+        gemm(UG_HEAD_E, 0, m->xa, E, W + o.wl, d.size_s, ep, false);
+    }
+    mark(m, st, nullptr);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { m->set_error(std::string("kernel launch: ") + cudaGetErrorString(e)); return TIP_ERR_CUDA; }
+    return TIP_OK;
+}
+
+extern "C" int tip_forward(tip_model* m, const float* x_imu, const float* x_s, float* y, int B, int L,
+                           const float* keep_mask, float past_scale, const tip_dropout* drop, void* stream_) {
+    if (!m) return TIP_ERR_INVALID_ARG;
+    if (!m->packed) { m->set_error("tip_forward before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
+    if (!x_imu || !x_s || !y || B < 1 || L < 1 || L > MAXL) {
+        m->set_error("tip_forward: need non-null tensors, B >= 1 and 1 <= L <= 40");
+        return TIP_ERR_INVALID_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream_;
+    TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    m->launches = 0;
+    const Dims& d = m->d;
+    for (int b0 = 0; b0 < B; b0 += CHUNK_WINDOWS) {
+        const int nb = std::min(CHUNK_WINDOWS, B - b0);
+        const size_t r0 = (size_t)b0 * L;
+        int rc = forward_chunk(m, x_imu + r0 * d.n_imu, x_s + r0 * d.size_s, y + r0 * d.size_s, nb, L,
+                               keep_mask ? keep_mask + r0 * d.size_s : nullptr, past_scale, drop, st);
+        if (rc != TIP_OK) return rc;
+    }
+    return TIP_OK;
+}
+
+extern "C" int tip_forward_host(tip_model* m, const float* x_imu_h, const float* x_s_h, float* y_h, int B,
+                                int L, int last_row_only, const tip_dropout* drop, void* stream_) {
+    if (!m) return TIP_ERR_INVALID_ARG;
+    if (!x_imu_h || !x_s_h || !y_h || B < 1 || L < 1 || L > MAXL) {
+        m->set_error("tip_forward_host: bad arguments");
+        return TIP_ERR_INVALID_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream_;
+    TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    const Dims& d = m->d;
+    const size_t rows = (size_t)B * L;
+    if (rows > m->host_cap) {
+        for (float* p : {m->d_ximu, m->d_xs, m->d_y}) if (p) cudaFree(p);
+        for (float* p : {m->h_in, m->h_out}) if (p) cudaFreeHost(p);
+        m->host_cap = 0;
+        const size_t cap = align_up(rows, 64);
+        TIP_CUDA_TRY(m, cudaMalloc(&m->d_ximu, cap * d.n_imu * sizeof(float)));
+        TIP_CUDA_TRY(m, cudaMalloc(&m->d_xs, cap * d.size_s * sizeof(float)));
+        TIP_CUDA_TRY(m, cudaMalloc(&m->d_y, cap * d.size_s * sizeof(float)));
+        TIP_CUDA_TRY(m, cudaMallocHost(&m->h_in, cap * d.d_in * sizeof(float)));
+        TIP_CUDA_TRY(m, cudaMallocHost(&m->h_out, cap * d.size_s * sizeof(float)));
+        m->host_cap = cap;
+    }
+    float* h_imu = m->h_in;
+    float* h_s = m->h_in + rows * d.n_imu;
+    memcpy(h_imu, x_imu_h, rows * d.n_imu * sizeof(float));
+    memcpy(h_s, x_s_h, rows * d.size_s * sizeof(float));
+    TIP_CUDA_TRY(m, cudaMemcpyAsync(m->d_ximu, h_imu, rows * d.n_imu * sizeof(float), cudaMemcpyHostToDevice, st));
+    TIP_CUDA_TRY(m, cudaMemcpyAsync(m->d_xs, h_s, rows * d.size_s * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = tip_forward(m, m->d_ximu, m->d_xs, m->d_y, B, L, nullptr, 1.f, drop, st);
+    if (rc != TIP_OK) return rc;
+    if (last_row_only) {
+        // reuse the head of d_ximu as (B, size_s) scratch is unsafe (inputs live there); use d_xs tail-free buffer d_xs
+        last_row_kernel<<<(B * d.size_s + 255) / 256, 256, 0, st>>>(m->d_y, m->d_xs, B, L, d.size_s);
+        m->launches++;
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->h_out, m->d_xs, (size_t)B * d.size_s * sizeof(float), cudaMemcpyDeviceToHost, st));
+        TIP_CUDA_TRY(m, cudaStreamSynchronize(st));
+        memcpy(y_h, m->h_out, (size_t)B * d.size_s * sizeof(float));
+    } else {
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->h_out, m->d_y, rows * d.size_s * sizeof(float), cudaMemcpyDeviceToHost, st));
+        TIP_CUDA_TRY(m, cudaStreamSynchronize(st));
+        memcpy(y_h, m->h_out, rows * d.size_s * sizeof(float));
+    }
+    return TIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int tip_stream_reset(tip_model* m, int n_streams) {
+    if (!m || n_streams < 1) return TIP_ERR_INVALID_ARG;
+    TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    free_stream_state(m);
+    const Dims& d = m->d;
+    const size_t S = n_streams;
+    TIP_CUDA_TRY(m, cudaMalloc(&m->win_imu, S * MAXL * d.n_imu * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMalloc(&m->win_s, S * MAXL * d.size_s * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMalloc(&m->st_rows, S * d.d_in * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMalloc(&m->st_ximu, S * MAXL * d.n_imu * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMalloc(&m->st_xs, S * MAXL * d.size_s * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMalloc(&m->st_y, S * MAXL * d.size_s * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMalloc(&m->st_ylast, S * d.size_s * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMallocHost(&m->h_rows, S * d.d_in * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMallocHost(&m->h_ylast, S * d.size_s * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMemset(m->win_imu, 0, S * MAXL * d.n_imu * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMemset(m->win_s, 0, S * MAXL * d.size_s * sizeof(float)));
+    m->n_streams = n_streams;
+    m->stream_len = 0;
+    return TIP_OK;
+}
+
+extern "C" int tip_stream_length(const tip_model* m) { return m ? m->stream_len : 0; }
+
+// device work of one streaming step; inputs already in st_rows (imu rows then s rows)
+static int stream_step_device(tip_model* m, const tip_dropout* drop, cudaStream_t st, int len_before) {
+    const Dims& d = m->d;
+    const int S = m->n_streams;
+    const float* imu_rows = m->st_rows;
+    const float* s_rows = m->st_rows + (size_t)S * d.n_imu;
+    window_push_kernel<<<S, 256, 0, st>>>(m->win_imu, imu_rows, d.n_imu, len_before);
+    window_push_kernel<<<S, 256, 0, st>>>(m->win_s, s_rows, d.size_s, len_before);
+    m->launches += 2;
+    const int L = std::min(len_before + 1, MAXL);
+    const float *xi = m->win_imu, *xs = m->win_s;
+    int extra = 2;
+    if (L < MAXL) {
+        const int64_t ti = (int64_t)S * L * d.n_imu, ts = (int64_t)S * L * d.size_s;
+        window_compact_kernel<<<(unsigned)std::min<int64_t>((ti + 255) / 256, 1184), 256, 0, st>>>(m->win_imu, m->st_ximu, S, L, d.n_imu);
+        window_compact_kernel<<<(unsigned)std::min<int64_t>((ts + 255) / 256, 1184), 256, 0, st>>>(m->win_s, m->st_xs, S, L, d.size_s);
+        xi = m->st_ximu; xs = m->st_xs;
+        extra += 2;
+    }
+    int rc = tip_forward(m, xi, xs, m->st_y, S, L, nullptr, 1.f, drop, st);   // resets m->launches
+    if (rc != TIP_OK) return rc;
+    last_row_kernel<<<(S * d.size_s + 255) / 256, 256, 0, st>>>(m->st_y, m->st_ylast, S, L, d.size_s);
+    m->launches += extra + 1;
+    return TIP_OK;
+}
+
+extern "C" int tip_stream_step(tip_model* m, const float* imu_row, const float* s_row, float* y_last,
+                               int rows_on_host, const tip_dropout* drop, void* stream_) {
+    if (!m || !imu_row || !s_row || !y_last) return TIP_ERR_INVALID_ARG;
+    if (!m->packed) { m->set_error("tip_stream_step before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
+    if (m->n_streams < 1) { m->set_error("tip_stream_step before tip_stream_reset"); return TIP_ERR_INVALID_ARG; }
+    cudaStream_t st = (cudaStream_t)stream_;
+    TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    const Dims& d = m->d;
+    const size_t S = m->n_streams;
+    const size_t n_i = S * d.n_imu, n_s = S * d.size_s;
+    if (rows_on_host) {
+        memcpy(m->h_rows, imu_row, n_i * sizeof(float));
+        memcpy(m->h_rows + n_i, s_row, n_s * sizeof(float));
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows, m->h_rows, (n_i + n_s) * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows, imu_row, n_i * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows + n_i, s_row, n_s * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    const int len_before = m->stream_len;
+    const bool stochastic = drop && (drop->in_dropout > 0.f || drop->past_state_dropout > 0.f || drop->encoder_dropout > 0.f);
+    const bool steady = (len_before == MAXL);
+    int rc = TIP_OK;
+    if (steady && m->use_graphs && !stochastic) {
+        // steady state: the whole frame (2 window shifts + forward + last-row gather) is one graph launch
+        if (!m->st_graph) {
+            rc = ensure_workspace(m, (int)S * MAXL);
+            if (rc != TIP_OK) return rc;
+            if ((m->engine == 2 || (m->engine == 0 && UMMA_AVAILABLE && (int)S * MAXL >= 512)) && !m->maps_ready) {
+                // descriptors must exist before capture (their creation is host work)
+                rc = umma_build_maps(m->maps, m->blob, m->off, m->d, m->xin, m->plane_xin, m->xa, m->xb, m->att,
+                                     m->plane_e, m->hid, m->plane_f, m->hs, m->plane_r, m->cap_rows, m->err);
+                if (rc != TIP_OK) return rc;
+                m->maps_ready = true;
+            }
+            cudaStream_t cs;
+            TIP_CUDA_TRY(m, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            cudaGraph_t g = nullptr;
+            TIP_CUDA_TRY(m, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+            rc = stream_step_device(m, nullptr, cs, MAXL);
+            cudaError_t ce = cudaStreamEndCapture(cs, &g);
+            if (rc == TIP_OK && ce == cudaSuccess) {
+                ce = cudaGraphInstantiate(&m->st_graph, g, 0);
+                m->st_graph_launches = m->launches;
+            }
+            if (g) cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
+            if (rc != TIP_OK) return rc;
+            if (ce != cudaSuccess) { m->set_error(std::string("graph capture: ") + cudaGetErrorString(ce)); return TIP_ERR_CUDA; }
+        }
+        TIP_CUDA_TRY(m, cudaGraphLaunch(m->st_graph, st));
+        m->launches = m->st_graph_launches;
+    } else {
+        rc = stream_step_device(m, drop, st, len_before);
+        if (rc != TIP_OK) return rc;
+    }
+    m->stream_len = std::min(len_before + 1, MAXL);
+    if (rows_on_host) {
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->h_ylast, m->st_ylast, n_s * sizeof(float), cudaMemcpyDeviceToHost, st));
+        TIP_CUDA_TRY(m, cudaStreamSynchronize(st));
+        memcpy(y_last, m->h_ylast, n_s * sizeof(float));
+    } else {
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(y_last, m->st_ylast, n_s * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    return TIP_OK;
+}

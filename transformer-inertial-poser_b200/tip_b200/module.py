@@ -1,0 +1,289 @@
+"""Python mirror of the reference's model-call surface for the TIP hot path.
+
+``TF_RNN_Past_State`` here keeps the constructor, the 56-key ``state_dict`` and the
+``forward(x_imu, x_s)`` contract of the reference class
+(/root/reference/simple_transformer_with_state.py:8-102) so the reference's consumers
+(offline_testing_simple.py:79-99, live_demo_new.py:202-212, real_time_runner_minimal.py:149,
+real_time_runner.py:431) can import it by the same module name and run unmodified.  All
+arithmetic happens in ``libtip_b200.so`` (hand-written sm_100a kernels behind the C ABI of
+``include/tip_b200.h``); torch is used for parameter storage, device memory and streams only.
+There is no CPU path: calling the module with CPU tensors raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+from torch import nn
+
+from . import capi
+
+
+def state_dict_keys(tf_layers: int = 4, with_rnn: bool = True):
+    """Key order of the reference module's state_dict (56 tensors for the shipped checkpoints);
+    tip_pack_weights takes its pointers in this order."""
+    keys = ["in_linear.weight", "in_linear.bias"]
+    for i in range(tf_layers):
+        p = f"tf_encode.layers.{i}."
+        keys += [p + s for s in ("self_attn.in_proj_weight", "self_attn.in_proj_bias",
+                                 "self_attn.out_proj.weight", "self_attn.out_proj.bias",
+                                 "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias",
+                                 "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias")]
+    if with_rnn:
+        keys += ["rnn.weight_ih_l0", "rnn.weight_hh_l0", "rnn.bias_ih_l0", "rnn.bias_hh_l0"]
+    return keys + ["linear.weight", "linear.bias"]
+
+
+class _Bag(nn.Module):
+    """Parameter container; exists only so state_dict keys match the reference's."""
+
+
+def _linear_bag(n_out: int, n_in: int, gen: torch.Generator) -> _Bag:
+    b = _Bag()
+    bound = 1.0 / math.sqrt(n_in)
+    b.weight = nn.Parameter((torch.rand(n_out, n_in, generator=gen) * 2 - 1) * bound)
+    b.bias = nn.Parameter((torch.rand(n_out, generator=gen) * 2 - 1) * bound)
+    return b
+
+
+def _norm_bag(n: int) -> _Bag:
+    b = _Bag()
+    b.weight = nn.Parameter(torch.ones(n))
+    b.bias = nn.Parameter(torch.zeros(n))
+    return b
+
+
+class TF_RNN_Past_State(nn.Module):
+    """Drop-in for the reference class of the same name (reference :8).
+
+    Stochastic behaviour follows the reference as shipped: ``past_state_dropout`` and
+    ``in_dropout`` are applied on EVERY call (the reference builds fresh ``nn.Dropout`` modules,
+    :73/:77, which ignore ``eval()``), the encoder's p=0.1 dropouts only in ``train()`` mode.  The
+    masks come from a counter-based generator seeded from torch's CPU generator (so
+    ``torch.manual_seed`` makes runs repeatable) -- statistically equivalent to, not bit-equal
+    with, torch's Philox stream.  Deterministic parity mode: ``m.eval()`` and
+    ``m.past_state_dropout = 0.0``.
+    """
+
+    ENCODER_DROPOUT = 0.1   # nn.TransformerEncoderLayer default; the reference never overrides it (:26-28)
+
+    def __init__(self, input_size_imu, size_s, rnn_hid_size, tf_hid_size, tf_in_dim, n_heads,
+                 tf_layers, dropout, in_dropout, past_state_dropout, with_rnn=True,
+                 with_acc_sum=False):
+        super().__init__()
+        gen = torch.Generator().manual_seed(torch.initial_seed() & 0x7FFFFFFF)
+        d_in = input_size_imu + size_s + (18 if with_acc_sum else 0)
+        if with_acc_sum:
+            print("model with acc sum")                      # reference :21
+        self.in_linear = _linear_bag(tf_in_dim, d_in, gen)
+        self.tf_encode = _Bag()
+        self.tf_encode.layers = nn.ModuleList()
+        for _ in range(tf_layers):
+            layer = _Bag()
+            layer.self_attn = _Bag()
+            qkv = _linear_bag(3 * tf_in_dim, tf_in_dim, gen)
+            layer.self_attn.in_proj_weight = qkv.weight
+            layer.self_attn.in_proj_bias = qkv.bias
+            layer.self_attn.out_proj = _linear_bag(tf_in_dim, tf_in_dim, gen)
+            layer.linear1 = _linear_bag(tf_hid_size, tf_in_dim, gen)
+            layer.linear2 = _linear_bag(tf_in_dim, tf_hid_size, gen)
+            layer.norm1 = _norm_bag(tf_in_dim)
+            layer.norm2 = _norm_bag(tf_in_dim)
+            self.tf_encode.layers.append(layer)
+        self.with_rnn = with_rnn
+        if with_rnn:
+            self.rnn = _Bag()
+            ih = _linear_bag(rnn_hid_size, tf_in_dim, gen)
+            hh = _linear_bag(rnn_hid_size, rnn_hid_size, gen)
+            self.rnn.weight_ih_l0, self.rnn.weight_hh_l0 = ih.weight, hh.weight
+            self.rnn.bias_ih_l0, self.rnn.bias_hh_l0 = ih.bias, hh.bias
+            self.linear = _linear_bag(size_s, rnn_hid_size, gen)
+        else:
+            print("no RNN layer")                            # reference :44
+            self.rnn = None
+            self.linear = _linear_bag(size_s, tf_in_dim, gen)
+
+        self.rnn_hid_size = rnn_hid_size
+        self.in_dropout = in_dropout
+        self.n_heads = n_heads
+        self.past_state_dropout = past_state_dropout
+        print("number of parameters: %e", sum(p.numel() for p in self.parameters()))   # :54
+
+        self._dims = capi.TipDims(input_size_imu, size_s, rnn_hid_size, tf_hid_size, tf_in_dim,
+                                  n_heads, tf_layers, int(bool(with_rnn)), int(bool(with_acc_sum)))
+        self._size_s = size_s
+        self._n_imu = input_size_imu + (18 if with_acc_sum else 0)
+        self._lib = None
+        self._handle = None
+        self._device = None
+        self._packed_sig = None
+        self._plist = None
+
+    # -------------------------------------------------------------------------------------------
+    def _ordered_params(self):
+        """The tensors in the reference's state_dict() order (= tip_pack_weights order)."""
+        if self._plist is None:     # Parameter objects are stable across load_state_dict / .cuda()
+            sd = self.state_dict(keep_vars=True)
+            self._plist = [sd[k] for k in state_dict_keys(self._dims.tf_layers,
+                                                          bool(self._dims.with_rnn))]
+        return self._plist
+
+    def _release(self):
+        if self._handle is not None and self._lib is not None:
+            self._lib.tip_destroy(self._handle)
+        self._handle = None
+        self._packed_sig = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _ensure(self, device: torch.device):
+        """Create the C handle on ``device`` and (re)pack when any parameter changed
+        (load_state_dict, .cuda(), in-place optimiser updates bump ``_version``)."""
+        if self._lib is None:
+            self._lib = capi.load_library()
+        if self._handle is None or self._device != device:
+            self._release()
+            with torch.cuda.device(device):
+                h = C.c_void_p()
+                rc = self._lib.tip_create(C.byref(self._dims), C.byref(h))
+                capi.check(self._lib, None, rc, "tip_create")
+            self._handle, self._device = h, device
+        params = self._ordered_params()
+        sig = tuple((p.data_ptr(), p._version) for p in params)
+        if sig != self._packed_sig:
+            for p in params:
+                if p.device != device or p.dtype != torch.float32:
+                    raise RuntimeError(
+                        "TF_RNN_Past_State: parameters must be fp32 on the input's CUDA device "
+                        f"(got {p.dtype} on {p.device}; call .cuda() as the reference does)")
+            keep = [p.detach().contiguous() for p in params]
+            n = len(keep)
+            ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in keep])
+            numels = (C.c_int64 * n)(*[t.numel() for t in keep])
+            stream = torch.cuda.current_stream(device).cuda_stream
+            with torch.cuda.device(device):
+                rc = self._lib.tip_pack_weights(self._handle, ptrs, numels, n, C.c_void_p(stream))
+            capi.check(self._lib, self._handle, rc, "tip_pack_weights")
+            self._packed_sig = sig
+        return self._handle
+
+    def _dropout_struct(self):
+        p_enc = self.ENCODER_DROPOUT if self.training else 0.0
+        p_in, p_past = float(self.in_dropout), float(self.past_state_dropout)
+        if p_enc == 0.0 and p_in == 0.0 and p_past == 0.0:
+            return None
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        return capi.TipDropout(p_in, p_past, p_enc, seed & 0xFFFFFFFFFFFFFFFF)
+
+    def _check_inputs(self, x_imu, x_s):
+        if not (x_imu.is_cuda and x_s.is_cuda):
+            raise RuntimeError("TF_RNN_Past_State (tip_b200): inputs must be CUDA tensors; the "
+                               "B200 hot path has no CPU fallback")
+        if x_imu.dim() != 3 or x_s.dim() != 3 or x_imu.shape[:2] != x_s.shape[:2]:
+            raise RuntimeError(f"expected x_imu (B,L,{self._n_imu}) and x_s (B,L,{self._size_s}), "
+                               f"got {tuple(x_imu.shape)} and {tuple(x_s.shape)}")
+        if x_imu.shape[2] != self._n_imu or x_s.shape[2] != self._size_s:
+            raise RuntimeError(f"expected feature widths {self._n_imu} and {self._size_s}, got "
+                               f"{x_imu.shape[2]} and {x_s.shape[2]}")
+        return (x_imu.detach().to(torch.float32).contiguous(),
+                x_s.detach().to(torch.float32).contiguous())
+
+    def forward(self, x_imu, x_s, keep_mask=None, past_scale=1.0):
+        """(B, L, 72|90), (B, L, size_s) -> (B, L, size_s); reference :60-102.  Inputs are not
+        modified.  ``keep_mask`` (test hook): explicit 0/1 mask used instead of drawing the
+        past-state dropout mask; x_s is multiplied by keep_mask * past_scale."""
+        x_imu, x_s = self._check_inputs(x_imu, x_s)
+        dev = x_imu.device
+        h = self._ensure(dev)
+        B, L = x_imu.shape[0], x_imu.shape[1]
+        y = torch.empty((B, L, self._size_s), dtype=torch.float32, device=dev)
+        if B == 0:
+            return y
+        drop = self._dropout_struct()
+        km = None
+        if keep_mask is not None:
+            km = keep_mask.detach().to(device=dev, dtype=torch.float32).contiguous()
+            if drop is not None:
+                drop.past_state_dropout = 0.0
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = self._lib.tip_forward(h, x_imu.data_ptr(), x_s.data_ptr(), y.data_ptr(), B, L,
+                                       km.data_ptr() if km is not None else None,
+                                       float(past_scale), C.byref(drop) if drop else None,
+                                       C.c_void_p(stream))
+        capi.check(self._lib, h, rc, "tip_forward")
+        return y
+
+    # ---- extras beyond the reference surface --------------------------------------------------
+    def forward_host(self, x_imu, x_s, last_row_only=False):
+        """``model(x_imu.cuda(), x_s.cuda()).cpu()`` in one C call with host (numpy / CPU tensor)
+        buffers: H2D, forward, D2H, stream sync (real_time_runner_minimal.py:149).  Runs on the
+        device the parameters live on."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("forward_host: move the module to a CUDA device first (.cuda())")
+        h = self._ensure(dev)
+        xi = torch.as_tensor(x_imu, dtype=torch.float32).contiguous()
+        xs = torch.as_tensor(x_s, dtype=torch.float32).contiguous()
+        B, L = xi.shape[0], xi.shape[1]
+        y = torch.empty((B, self._size_s) if last_row_only else (B, L, self._size_s),
+                        dtype=torch.float32)
+        drop = self._dropout_struct()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = self._lib.tip_forward_host(h, xi.data_ptr(), xs.data_ptr(), y.data_ptr(), B, L,
+                                            int(last_row_only), C.byref(drop) if drop else None,
+                                            C.c_void_p(stream))
+        capi.check(self._lib, h, rc, "tip_forward_host")
+        return y
+
+    def set_gemm_engine(self, engine: int):
+        """0 auto, 1 FFMA fp32, 2 tcgen05 3xTF32 (tip_set_gemm_engine)."""
+        dev = next(self.parameters()).device
+        h = self._ensure(dev)
+        capi.check(self._lib, h, self._lib.tip_set_gemm_engine(h, int(engine)), "tip_set_gemm_engine")
+
+    def algorithmic_cost(self, B: int, L: int):
+        """(bytes, flops) of one forward as SURVEY.md 8d defines them."""
+        dev = next(self.parameters()).device
+        h = self._ensure(dev)
+        b, f = C.c_double(), C.c_double()
+        capi.check(self._lib, h, self._lib.tip_algorithmic_cost(h, B, L, C.byref(b), C.byref(f)),
+                   "tip_algorithmic_cost")
+        return b.value, f.value
+
+    def set_profile(self, enable: bool):
+        dev = next(self.parameters()).device
+        h = self._ensure(dev)
+        capi.check(self._lib, h, self._lib.tip_set_profile(h, int(enable)), "tip_set_profile")
+
+    def profile(self):
+        """[(stage name, layer, milliseconds)] of the last forward (needs set_profile(True))."""
+        out = []
+        buf = C.create_string_buffer(64)
+        for i in range(self._lib.tip_profile_stages(self._handle)):
+            layer, ms = C.c_int(), C.c_float()
+            rc = self._lib.tip_profile_get(self._handle, i, buf, 64, C.byref(layer), C.byref(ms))
+            capi.check(self._lib, self._handle, rc, "tip_profile_get")
+            out.append((buf.value.decode(), layer.value, ms.value))
+        return out
+
+    def last_launch_count(self) -> int:
+        return int(self._lib.tip_last_launch_count(self._handle)) if self._handle else 0
+
+    def debug_tensor(self, name: str, cols: int):
+        """Copy of an internal activation buffer of the last forward (test hook)."""
+        n = C.c_int64()
+        rc = self._lib.tip_debug_tensor(self._handle, name.encode(), None, 0, C.byref(n), None)
+        capi.check(self._lib, self._handle, rc, "tip_debug_tensor")
+        out = torch.empty(n.value, dtype=torch.float32, device=self._device)
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        rc = self._lib.tip_debug_tensor(self._handle, name.encode(), out.data_ptr(), n.value,
+                                        C.byref(n), C.c_void_p(stream))
+        capi.check(self._lib, self._handle, rc, "tip_debug_tensor")
+        return out.view(-1, cols)
