@@ -1,20 +1,474 @@
-// tcgen05 3xTF32 GEMM engine (placeholder interface; filled in by tip_umma.cuh proper).
+// tcgen05 GEMM engine of the TIP hot path (sm_100a): C[M,N] = A[M,K] * W[N,K]^T with fp32-parity
+// accuracy from three TF32 tensor-core products per tile (error-compensated split,
+// a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with hi = rna_tf32(x), lo = rna_tf32(x - hi); a single
+// TF32 pass misses the 1e-4 parity bar by 100x).
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0      TMA producer   : cp.async.bulk.tensor 2D tiles (128B-swizzled, K-major) of the four
+//                                operand planes into a multi-stage shared-memory ring (mbarrier
+//                                complete_tx)
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8),
+//                                3 per k-step, accumulating in TMEM; tcgen05.commit frees the smem
+//                                stage / publishes the accumulator
+//   warps 2..5  epilogue       : tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next
+//                                tile's MMAs overlap), fused bias / ReLU / dropout, or residual +
+//                                LayerNorm over the full 256-wide row, optional TF32 hi/lo split of
+//                                the output for the next GEMM, coalesced-by-row global stores.
 #pragma once
+#include <cuda.h>
+
 #include "tip_common.cuh"
 #include "tip_simt.cuh"
 
 namespace tip {
 
 enum UmmaGemmId { UG_IN = 0, UG_QKV, UG_OUT, UG_FF1, UG_FF2, UG_IH, UG_HEAD_R, UG_HEAD_E, UG_COUNT };
+constexpr bool UMMA_AVAILABLE = true;
 
-constexpr bool UMMA_AVAILABLE = false;
-struct UmmaMaps { int dummy = 0; };
+constexpr int UM_BM = 128;          // UMMA M (cta_group::1)
+constexpr int UM_BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UM_THREADS = 192;
 
-inline int umma_build_maps(UmmaMaps&, const float*, const PackOff&, const Dims&, float*, size_t, float*, float*,
-                           float*, size_t, float*, size_t, float*, size_t, int, std::string& err) {
-    err = "tcgen05 engine not built";
-    return TIP_ERR_INVALID_ARG;
+template <int BN> struct UmmaCfg {
+    static constexpr int STAGES = (BN == 256) ? 2 : 3;
+    static constexpr int A_BYTES = UM_BM * 128;                 // one plane of A per stage
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+    static constexpr int TMEM_COLS = 2 * BN;                    // double-buffered accumulator
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-inline void umma_gemm(UmmaMaps&, int, int, int, int, int, const Epi&, bool, cudaStream_t) {}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait: a protocol bug traps (surfaces as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t gets row (lane base + t), columns c..c+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr),
+          "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+}  // namespace ptx
+
+// K-major, 128B-swizzled shared-memory operand descriptor (tile rows x 128 bytes, 8-row groups
+// 1024 bytes apart).  Bit layout: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+// layout type SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::tf32 instruction descriptor: D fp32 (bits 4-5 = 1), A/B TF32 (format 2 at bits 7-9 / 10-12),
+// both K-major, N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, bool LN>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                 const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+                 int M, int N, int K, Epi ep) {
+    using Cfg = UmmaCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]       MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (N + BN - 1) / BN;
+    const int m_tiles = (M + UM_BM - 1) / UM_BM;
+    const int total_tiles = n_tiles * m_tiles;
+    const int num_kb = K / UM_BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&mapA_hi); ptx::prefetch_tmap(&mapA_lo);
+        ptx::prefetch_tmap(&mapB_hi); ptx::prefetch_tmap(&mapB_lo);
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * UM_BM, n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
+                    ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    ptx::tma_load_2d(s, &mapA_hi, &full_bar[stage], kb * UM_BK, m0);
+                    ptx::tma_load_2d(s + Cfg::A_BYTES, &mapA_lo, &full_bar[stage], kb * UM_BK, m0);
+                    ptx::tma_load_2d(s + 2 * Cfg::A_BYTES, &mapB_hi, &full_bar[stage], kb * UM_BK, n0);
+                    ptx::tma_load_2d(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, &full_bar[stage], kb * UM_BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(UM_BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t a_hi = umma_smem_desc(sa), a_lo = umma_smem_desc(sa + Cfg::A_BYTES);
+                    const uint64_t b_hi = umma_smem_desc(sa + 2 * Cfg::A_BYTES);
+                    const uint64_t b_lo = umma_smem_desc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < UM_BK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 8 tf32 = 32 bytes along K
+                        ptx::umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                        ptx::umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                        ptx::umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);          // smem stage free once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tfull_bar[as]);                 // accumulator complete
+            }
+        }
+    } else {
+        // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
+        const int quarter = warp & 3;
+        const float inv_keep = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int m0 = (tile / n_tiles) * UM_BM, n0 = (tile % n_tiles) * BN;
+            const int row = m0 + quarter * 32 + lane;
+            const bool row_ok = row < M;
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+            float v[32];
+            if constexpr (LN) {
+                // pass 1: x = acc + bias (dropout) + residual, kept in TMEM; row sum
+                float s = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    ptx::tmem_ld32(t_acc + c * 32, v);
+                    const float* rp = ep.resid + (size_t)row * ep.ldr + c * 32;
+                    const float* rl = ep.resid_lo ? ep.resid_lo + (size_t)row * ep.ldr + c * 32 : nullptr;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row_ok) {
+                            r = __ldg(reinterpret_cast<const float4*>(rp) + j4);
+                            if (rl) {
+                                const float4 l = __ldg(reinterpret_cast<const float4*>(rl) + j4);
+                                r.x += l.x; r.y += l.y; r.z += l.z; r.w += l.w;
+                            }
+                        }
+                        const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int j = j4 * 4 + q, col = c * 32 + j;
+                            float x = v[j] + __ldg(ep.bias + col);
+                            if (ep.drop_p > 0.f) x *= dropout_factor(ep.drop_p, inv_keep, ep.seed, (uint64_t)row * N + col);
+                            x += rr[q];
+                            v[j] = x;
+                            s += x;
+                        }
+                    }
+                    ptx::tmem_st32(t_acc + c * 32, v);
+                }
+                const float mean = s * (1.f / BN);
+                float q2 = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    ptx::tmem_ld32(t_acc + c * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; q2 = fmaf(d, d, q2); }
+                }
+                const float rstd = rsqrtf(q2 * (1.f / BN) + 1e-5f);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    ptx::tmem_ld32(t_acc + c * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = c * 32 + j;
+                        v[j] = (v[j] - mean) * rstd * __ldg(ep.gamma + col) + __ldg(ep.beta + col);
+                    }
+                    if (row_ok) {
+                        float* o = ep.out + (size_t)row * ep.ldc + c * 32;
+                        float* ol = ep.out_lo ? ep.out_lo + (size_t)row * ep.ldc + c * 32 : nullptr;
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            if (ol) {
+                                float4 hi, lo;
+                                tf32_split(v[j4 * 4 + 0], hi.x, lo.x); tf32_split(v[j4 * 4 + 1], hi.y, lo.y);
+                                tf32_split(v[j4 * 4 + 2], hi.z, lo.z); tf32_split(v[j4 * 4 + 3], hi.w, lo.w);
+                                reinterpret_cast<float4*>(o)[j4] = hi;
+                                reinterpret_cast<float4*>(ol)[j4] = lo;
+                            } else {
+                                reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                            }
+                        }
+                    }
+                }
+            } else {
+                const bool vec_ok = (ep.ldc & 3) == 0;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int colb = n0 + c * 32;
+                    if (colb >= N) break;                         // warp-uniform
+                    ptx::tmem_ld32(t_acc + c * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = colb + j;
+                        float x = v[j] + ((col < N) ? __ldg(ep.bias + col) : 0.f);
+                        if (ep.relu) x = fmaxf(x, 0.f);
+                        if (ep.drop_p > 0.f) x *= dropout_factor(ep.drop_p, inv_keep, ep.seed, (uint64_t)row * N + col);
+                        v[j] = x;
+                    }
+                    if (row_ok) {
+                        float* o = ep.out + (size_t)row * ep.ldc + colb;
+                        float* ol = ep.out_lo ? ep.out_lo + (size_t)row * ep.ldc + colb : nullptr;
+                        if (vec_ok && colb + 32 <= N) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                if (ol) {
+                                    float4 hi, lo;
+                                    tf32_split(v[j4 * 4 + 0], hi.x, lo.x); tf32_split(v[j4 * 4 + 1], hi.y, lo.y);
+                                    tf32_split(v[j4 * 4 + 2], hi.z, lo.z); tf32_split(v[j4 * 4 + 3], hi.w, lo.w);
+                                    reinterpret_cast<float4*>(o)[j4] = hi;
+                                    reinterpret_cast<float4*>(ol)[j4] = lo;
+                                } else {
+                                    reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (colb + j < N) {
+                                    if (ol) { float hi, lo; tf32_split(v[j], hi, lo); o[j] = hi; ol[j] = lo; }
+                                    else o[j] = v[j];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);     // 4 arrivals free the accumulator
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: TMA descriptors of every operand plane and the launch table.
+struct UmmaOperand { CUtensorMap hi, lo; };
+struct UmmaMaps {
+    UmmaOperand a_xin, a_xa, a_xb, a_att, a_hid, a_hs;                    // activations (box 32 x 128)
+    UmmaOperand w_in, w_qkv[MAX_LAYERS], w_o[MAX_LAYERS], w_1[MAX_LAYERS], w_2[MAX_LAYERS], w_ih, w_l;
+    int num_sms = 148;
+    bool attrs_set = false;
+};
+
+typedef CUresult (*tip_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+inline tip_encode_tiled_fn umma_encode_fn() {
+    static tip_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tip_encode_tiled_fn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major [rows][cols] plane, box = 32 columns (128 bytes, swizzled) x box_rows rows
+inline bool umma_make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    tip_encode_tiled_fn enc = umma_encode_fn();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)UM_BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, const Dims& d, float* xin,
+                           size_t plane_xin, float* xa, float* xb, float* att, size_t plane_e, float* hid,
+                           size_t plane_f, float* hs, size_t plane_r, int cap_rows, std::string& err) {
+    bool ok = true;
+    auto act = [&](UmmaOperand& op, const float* p, size_t plane, int cols) {
+        ok = ok && umma_make_map(&op.hi, p, cap_rows, cols, UM_BM) && umma_make_map(&op.lo, p + plane, cap_rows, cols, UM_BM);
+    };
+    auto wgt = [&](UmmaOperand& op, size_t hi, size_t lo, int rows, int cols, int bn) {
+        ok = ok && umma_make_map(&op.hi, blob + hi, rows, cols, bn) && umma_make_map(&op.lo, blob + lo, rows, cols, bn);
+    };
+    act(mp.a_xin, xin, plane_xin, d.kin_pad);
+    act(mp.a_xa, xa, plane_e, E);
+    act(mp.a_xb, xb, plane_e, E);
+    act(mp.a_att, att, plane_e, E);
+    act(mp.a_hid, hid, plane_f, F);
+    act(mp.a_hs, hs, plane_r, R);
+    wgt(mp.w_in, o.win_hi, o.win_lo, E, d.kin_pad, 128);
+    for (int l = 0; l < d.layers; ++l) {
+        const LayerOff& L = o.layer[l];
+        wgt(mp.w_qkv[l], L.wqkv_hi, L.wqkv_lo, 3 * E, E, 128);
+        wgt(mp.w_o[l], L.wo_hi, L.wo_lo, E, E, 256);
+        wgt(mp.w_1[l], L.w1_hi, L.w1_lo, F, E, 128);
+        wgt(mp.w_2[l], L.w2_hi, L.w2_lo, E, F, 256);
+    }
+    if (d.with_rnn) wgt(mp.w_ih, o.wih_hi, o.wih_lo, R, E, 128);
+    wgt(mp.w_l, o.wl_hi, o.wl_lo, HEAD_NPAD, d.khead, 128);
+    if (!ok) { err = "cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor-map arguments)"; return TIP_ERR_CUDA; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&mp.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!mp.attrs_set) {
+        cudaFuncSetAttribute(umma_gemm_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
+        mp.attrs_set = true;
+    }
+    return TIP_OK;
+}
+
+inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, const Epi& ep, bool ln,
+                      cudaStream_t st) {
+    const UmmaOperand *A = nullptr, *B = nullptr;
+    switch (which) {
+        case UG_IN:     A = &mp.a_xin; B = &mp.w_in; break;
+        case UG_QKV:    A = &mp.a_xa;  B = &mp.w_qkv[layer]; break;
+        case UG_OUT:    A = &mp.a_att; B = &mp.w_o[layer]; break;
+        case UG_FF1:    A = &mp.a_xb;  B = &mp.w_1[layer]; break;
+        case UG_FF2:    A = &mp.a_hid; B = &mp.w_2[layer]; break;
+        case UG_IH:     A = &mp.a_xa;  B = &mp.w_ih; break;
+        case UG_HEAD_R: A = &mp.a_hs;  B = &mp.w_l; break;
+        default:        A = &mp.a_xa;  B = &mp.w_l; break;      // UG_HEAD_E
+    }
+    const int m_tiles = (M + UM_BM - 1) / UM_BM;
+    if (ln) {
+        const int tiles = m_tiles;                                // BN = 256 = the whole row
+        umma_gemm_kernel<256, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<256>::SMEM_BYTES, st>>>(
+            A->hi, A->lo, B->hi, B->lo, M, N, K, ep);
+    } else {
+        const int tiles = m_tiles * ((N + 127) / 128);
+        umma_gemm_kernel<128, false><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<128>::SMEM_BYTES, st>>>(
+            A->hi, A->lo, B->hi, B->lo, M, N, K, ep);
+    }
+}
 
 }  // namespace tip
