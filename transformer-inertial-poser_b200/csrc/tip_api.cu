@@ -12,6 +12,7 @@
 using namespace tip;
 
 namespace {
+unsigned long long* g_tbuf = nullptr;
 std::string g_create_error;
 constexpr int CHUNK_WINDOWS = 1024;   // windows per pass through the workspace
 }  // namespace
@@ -27,6 +28,8 @@ struct tip_model {
     int use_graphs = 1;
     int launches = 0;
     int64_t last_rows = 0;
+    int rnn_clusters = -1;          // co-schedulable 8-CTA clusters (queried on first use)
+    int rnn_stream_fallback = 0;    // TIP_RNN_STREAM=1: L2-streaming kernel (debug / comparison)
     std::string err;
 
     // workspace (capacity in rows)
@@ -34,7 +37,7 @@ struct tip_model {
     float* ws = nullptr;
     float *xin = nullptr, *xa = nullptr, *xb = nullptr, *qkv = nullptr, *att = nullptr,
           *hid = nullptr, *gi = nullptr, *hs = nullptr;
-    size_t plane_xin = 0, plane_e = 0, plane_f = 0, plane_r = 0;   // hi->lo plane strides (floats)
+    size_t plane_xin = 0, plane_e = 0, plane_f = 0, plane_r = 0;   // elements per plane (= hi->lo stride in halves)
     UmmaMaps maps;            // TMA descriptors of the workspace + weights (tcgen05 engine)
     bool maps_ready = false;
 
@@ -101,6 +104,7 @@ static void compute_offsets(tip_model* m) {
     }
     o.wl = take((size_t)HEAD_NPAD * d.khead); o.bl = take(HEAD_NPAD);
     o.wl_hi = take((size_t)HEAD_NPAD * d.khead); o.wl_lo = take((size_t)HEAD_NPAD * d.khead);
+    o.scales = take(2 * SC_COUNT);            // [SC_COUNT] epilogue factors, then [SC_COUNT] weight scales
     o.total = p;
 }
 
@@ -134,10 +138,11 @@ extern "C" int tip_create(const tip_dims* dims, tip_model** out) {
     m->d.n_imu = dims->input_size_imu + (dims->with_acc_sum ? 18 : 0);
     m->d.size_s = dims->size_s;
     m->d.d_in = m->d.n_imu + dims->size_s;
-    m->d.kin_pad = (int)align_up(m->d.d_in, 32);
+    m->d.kin_pad = (int)align_up(m->d.d_in, 64);
     m->d.layers = dims->tf_layers;
     m->d.with_rnn = dims->with_rnn ? 1 : 0;
     m->d.khead = dims->with_rnn ? R : E;
+    m->rnn_stream_fallback = getenv("TIP_RNN_STREAM") ? atoi(getenv("TIP_RNN_STREAM")) : 0;
     compute_offsets(m);
     cudaError_t e = cudaMalloc(&m->blob, m->off.total * sizeof(float));
     if (e != cudaSuccess) {
@@ -203,13 +208,18 @@ extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64
     auto copy = [&](size_t dst, const float* src, size_t cnt) {
         return cudaMemcpyAsync(B + dst, src, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st);
     };
-    auto split = [&](size_t src, size_t hi, size_t lo, size_t cnt) {
-        pack_split_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(B + src, B + hi, B + lo, (int64_t)cnt);
+    // FP16 hi/lo planes of s_w * W (s_w = power of two from max|W|) + the epilogue's 1/(s_w * s_a)
+    auto split = [&](size_t src, size_t hi, size_t lo, size_t cnt, int sc_idx, float act_scale) {
+        float* inv = B + o.scales + sc_idx;
+        float* wsc = B + o.scales + SC_COUNT + sc_idx;
+        pack_scale_kernel<<<1, 256, 0, st>>>(B + src, (int64_t)cnt, act_scale, inv, wsc);
+        pack_split_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(B + src, reinterpret_cast<__half*>(B + hi),
+                                                                        reinterpret_cast<__half*>(B + lo), (int64_t)cnt, wsc);
     };
     int i = 0;
     pack_in_linear_kernel<<<(E * d.kin_pad + 255) / 256, 256, 0, st>>>(t[0], t[1], B + o.win, B + o.bin,
                                                                      d.d_in, d.kin_pad, d.n_imu);
-    split(o.win, o.win_hi, o.win_lo, (size_t)E * d.kin_pad);
+    split(o.win, o.win_hi, o.win_lo, (size_t)E * d.kin_pad, SC_IN, 1.f);    // raw input planes carry scale 1
     i = 2;
     for (int l = 0; l < d.layers; ++l) {
         const LayerOff& L = o.layer[l];
@@ -227,10 +237,10 @@ extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64
         TIP_CUDA_TRY(m, copy(L.be1, t[i + 9], E));
         TIP_CUDA_TRY(m, copy(L.g2, t[i + 10], E));
         TIP_CUDA_TRY(m, copy(L.be2, t[i + 11], E));
-        split(L.wqkv, L.wqkv_hi, L.wqkv_lo, (size_t)3 * E * E);
-        split(L.wo, L.wo_hi, L.wo_lo, (size_t)E * E);
-        split(L.w1, L.w1_hi, L.w1_lo, (size_t)F * E);
-        split(L.w2, L.w2_hi, L.w2_lo, (size_t)E * F);
+        split(L.wqkv, L.wqkv_hi, L.wqkv_lo, (size_t)3 * E * E, SC_LAYER0 + 4 * l + 0, ACT_SCALE);
+        split(L.wo, L.wo_hi, L.wo_lo, (size_t)E * E, SC_LAYER0 + 4 * l + 1, ACT_SCALE);
+        split(L.w1, L.w1_hi, L.w1_lo, (size_t)F * E, SC_LAYER0 + 4 * l + 2, ACT_SCALE);
+        split(L.w2, L.w2_hi, L.w2_lo, (size_t)E * F, SC_LAYER0 + 4 * l + 3, ACT_SCALE);
         i += 12;
     }
     if (d.with_rnn) {
@@ -238,12 +248,12 @@ extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64
         TIP_CUDA_TRY(m, copy(o.whh, t[i + 1], (size_t)R * R));
         pack_transpose_kernel<<<dim3(R / 32, R / 32), dim3(32, 32), 0, st>>>(t[i + 1], B + o.whh_t, R);
         pack_add_kernel<<<(R + 255) / 256, 256, 0, st>>>(t[i + 2], t[i + 3], B + o.brnn, R);
-        split(o.wih, o.wih_hi, o.wih_lo, (size_t)R * E);
+        split(o.wih, o.wih_hi, o.wih_lo, (size_t)R * E, SC_IH, ACT_SCALE);
         i += 4;
     }
     pack_pad_rows_kernel<<<(HEAD_NPAD * d.khead + 255) / 256, 256, 0, st>>>(t[i], B + o.wl, d.size_s, HEAD_NPAD, d.khead);
     pack_pad_rows_kernel<<<1, 256, 0, st>>>(t[i + 1], B + o.bl, d.size_s, HEAD_NPAD, 1);
-    split(o.wl, o.wl_hi, o.wl_lo, (size_t)HEAD_NPAD * d.khead);
+    split(o.wl, o.wl_hi, o.wl_lo, (size_t)HEAD_NPAD * d.khead, SC_HEAD, ACT_SCALE);
     TIP_CUDA_TRY(m, cudaGetLastError());
     m->packed = true;
     m->maps_ready = false;
@@ -277,6 +287,10 @@ extern "C" int tip_set_use_graphs(tip_model* m, int enable) {
 }
 extern "C" int tip_last_launch_count(const tip_model* m) { return m ? m->launches : 0; }
 
+extern "C" int tip_debug_timestamps(unsigned long long* host_out, int n) {
+    if (!g_tbuf || n > 64 * 32) return TIP_ERR_INVALID_ARG;
+    return cudaMemcpy(host_out, g_tbuf, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? TIP_OK : TIP_ERR_CUDA;
+}
 extern "C" int tip_set_profile(tip_model* m, int enable) {
     if (!m) return TIP_ERR_INVALID_ARG;
     m->profile = enable ? 1 : 0;
@@ -342,9 +356,10 @@ static int ensure_workspace(tip_model* m, int rows) {
     m->plane_r = (size_t)cap * R;
     size_t p = 0;
     auto take = [&](size_t n) { size_t r = p; p = align_up(p + n, 256); return r; };
-    const size_t o_xin = take(2 * m->plane_xin), o_xa = take(2 * m->plane_e), o_xb = take(2 * m->plane_e),
-                 o_qkv = take((size_t)cap * 3 * E), o_att = take(2 * m->plane_e),
-                 o_hid = take(2 * m->plane_f), o_gi = take(m->plane_r), o_hs = take(2 * m->plane_r);
+    // one fp32 plane per activation; the tcgen05 engine uses the same bytes as two fp16 planes (hi, lo)
+    const size_t o_xin = take(m->plane_xin), o_xa = take(m->plane_e), o_xb = take(m->plane_e),
+                 o_qkv = take((size_t)cap * 3 * E), o_att = take(m->plane_e),
+                 o_hid = take(m->plane_f), o_gi = take(m->plane_r), o_hs = take(m->plane_r);
     cudaError_t e = cudaMalloc(&m->ws, p * sizeof(float));
     if (e != cudaSuccess) {
         m->set_error(std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e));
@@ -373,12 +388,37 @@ static void launch_sgemm(tip_model* m, cudaStream_t st, const float* A, int lda,
 
 static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, float* out, float* out_lo,
                              int B, int L, float drop_p, uint64_t seed) {
-    if (B >= 64) attention_kernel<1, 8><<<dim3(B, NH / 8), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
+    if (B >= 32) attention_kernel<2, 4><<<dim3(B, NH / 4), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
     else         attention_kernel<4, 2><<<dim3(B, NH / 2), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
     m->launches++;
 }
 
 static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs, float* hs_lo, int B, int L) {
+    if (m->rnn_clusters < 0) {
+        // how many 8-CTA clusters the device can co-schedule (GPC layout dependent; 16..18 on B200)
+        cudaFuncSetAttribute(rnn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RC_SMEM_BYTES);
+        cudaLaunchConfig_t q{};
+        q.gridDim = dim3(RC_CTAS * 18); q.blockDim = dim3(256); q.dynamicSmemBytes = RC_SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = RC_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        q.attrs = nullptr; q.numAttrs = 0;   // the kernel carries __cluster_dims__ itself
+        (void)at;
+        int n = 0;
+        cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, rnn_cluster_kernel, &q);
+        if (getenv("TIP_VERBOSE")) fprintf(stderr, "[tip] cudaOccupancyMaxActiveClusters -> %d (%s)\n", n, cudaGetErrorString(qe));
+        if (qe != cudaSuccess || n < 1) { n = 0; cudaGetLastError(); }
+        if (getenv("TIP_RNN_CLUSTERS")) n = atoi(getenv("TIP_RNN_CLUSTERS"));
+        if (getenv("TIP_VERBOSE")) fprintf(stderr, "[tip] rnn clusters co-schedulable: %d\n", n);
+        m->rnn_clusters = n;
+    }
+    if (m->rnn_clusters > 0 && !m->rnn_stream_fallback) {
+        const int blocks = (B + RC_ROWS - 1) / RC_ROWS;
+        const int nc = std::min(blocks, m->rnn_clusters);
+        rnn_cluster_kernel<<<nc * RC_CTAS, 256, RC_SMEM_BYTES, st>>>(gi, m->blob + m->off.whh, hs, hs_lo, B, L);
+        m->launches++;
+        return;
+    }
     const float* whh_t = m->blob + m->off.whh_t;
     if (B >= 8 * 64) rnn_stream_kernel<8><<<(B + 7) / 8, R, 0, st>>>(gi, whh_t, hs, hs_lo, B, L);
     else if (B >= 2 * 74) rnn_stream_kernel<2><<<(B + 1) / 2, R, 0, st>>>(gi, whh_t, hs, hs_lo, B, L);
@@ -410,12 +450,12 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
             m->maps_ready = true;
         }
     }
-    float* lo_xin = umma ? m->xin + m->plane_xin : nullptr;
-    float* lo_xa = umma ? m->xa + m->plane_e : nullptr;
-    float* lo_xb = umma ? m->xb + m->plane_e : nullptr;
-    float* lo_att = umma ? m->att + m->plane_e : nullptr;
-    float* lo_hid = umma ? m->hid + m->plane_f : nullptr;
-    float* lo_hs = umma ? m->hs + m->plane_r : nullptr;
+    float* lo_xin = umma ? m->xin + m->plane_xin / 2 : nullptr;
+    float* lo_xa = umma ? m->xa + m->plane_e / 2 : nullptr;
+    float* lo_xb = umma ? m->xb + m->plane_e / 2 : nullptr;
+    float* lo_att = umma ? m->att + m->plane_e / 2 : nullptr;
+    float* lo_hid = umma ? m->hid + m->plane_f / 2 : nullptr;
+    float* lo_hs = umma ? m->hs + m->plane_r / 2 : nullptr;
 
     m->st_names.clear();
     m->st_layers.clear();
@@ -429,6 +469,18 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
     }
     auto gemm = [&](int which, int layer, const float* A, int K, const float* Wp, int N, Epi ep, bool ln) {
         if (umma) {
+            const int sc = which == UG_IN ? SC_IN : which == UG_IH ? SC_IH : (which == UG_HEAD_R || which == UG_HEAD_E) ? SC_HEAD
+                           : SC_LAYER0 + 4 * layer + (which == UG_QKV ? 0 : which == UG_OUT ? 1 : which == UG_FF1 ? 2 : 3);
+            ep.acc_scale = W + o.scales + sc;
+            static const int dbg = getenv("TIP_DBG") ? atoi(getenv("TIP_DBG")) : 0;
+            ep.dbg = dbg;
+            ep.tbuf = nullptr;
+            if (dbg & 4) {
+                static unsigned long long* tb = nullptr;
+                if (!tb) cudaMalloc(&tb, 64 * 32 * sizeof(unsigned long long));
+                ep.tbuf = tb + 8 * (which + (layer > 0 ? 16 : 0));
+                g_tbuf = tb;
+            }
             umma_gemm(m->maps, which, layer, M, N, K, ep, ln, st);
             m->launches++;
         } else {

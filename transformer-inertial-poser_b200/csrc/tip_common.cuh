@@ -1,5 +1,6 @@
 // Shared definitions for the TIP hot-path kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -19,17 +20,26 @@ constexpr int MAXL = 40;      // runner's max_input_l (real_time_runner_minimal.
 constexpr int MAX_LAYERS = 8;
 constexpr int HEAD_NPAD = 144;  // size_s (<=144) padded to a legal UMMA N (multiple of 16)
 
-// Offsets (in floats) into the packed weight blob.  Every matrix exists as an fp32 plane and as a
-// TF32 hi/lo pair (hi = rna_tf32(w), lo = rna_tf32(w - hi)) for the tcgen05 3xTF32 GEMMs.
+// Offsets (in floats) into the packed weight blob.  Every matrix exists as an fp32 plane (FFMA
+// engine) and as an FP16 hi/lo pair of the power-of-two pre-scaled matrix, hi = fp16(s*w),
+// lo = fp16(s*w - hi), for the tcgen05 3xFP16 GEMMs (the *_hi/_lo offsets are float offsets of
+// __half planes; `scales` holds 1/(s_w * s_a) per matrix, read by the GEMM epilogue).
 struct LayerOff {
     size_t wqkv, bqkv, wo, bo, w1, b1, w2, b2, g1, be1, g2, be2;
     size_t wqkv_hi, wqkv_lo, wo_hi, wo_lo, w1_hi, w1_lo, w2_hi, w2_lo;
 };
+// index of a matrix in the `scales` table
+constexpr int SC_IN = 0, SC_LAYER0 = 1 /* + 4*layer + {qkv,o,1,2} */, SC_IH = 1 + 4 * MAX_LAYERS, SC_HEAD = SC_IH + 1,
+              SC_COUNT = SC_HEAD + 1;
+// activations are stored as FP16 hi/lo planes of ACT_SCALE * x (|x| < 4096 representable; the
+// model's LayerNorm / ReLU / tanh outputs stay below ~20), the raw model input with scale 1.
+constexpr float ACT_SCALE = 16.f;
 struct PackOff {
     size_t win, bin, win_hi, win_lo;          // [E][kin_pad]
     LayerOff layer[MAX_LAYERS];
     size_t wih, brnn, whh, whh_t, wih_hi, wih_lo;   // whh [R][R] (out,in);  whh_t [R k][R n]
     size_t wl, bl, wl_hi, wl_lo;              // head [HEAD_NPAD][khead] zero padded rows
+    size_t scales;                            // [SC_COUNT] accumulator un-scale factors
     size_t total;
 };
 
@@ -37,7 +47,7 @@ struct Dims {
     int n_imu;      // input_size_imu (+18 with acc sum)
     int size_s;
     int d_in;       // n_imu + size_s
-    int kin_pad;    // d_in rounded up to 32 (one 128-byte TMA/UMMA k-block of fp32)
+    int kin_pad;    // d_in rounded up to 64 (one 128-byte TMA/UMMA k-block of fp16)
     int layers;
     int with_rnn;
     int khead;      // R or E
@@ -58,14 +68,35 @@ __device__ __forceinline__ float dropout_factor(float p, float inv_keep, uint64_
     return ((float)r * 2.3283064365386963e-10f < p) ? 0.f : inv_keep;
 }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+// Error-compensated FP16 split of an (already scaled) fp32 value: v ~= hi + lo to ~22 bits.
+// The hi conversion saturates (|v| > 65504 clamps) so out-of-range inputs cannot inject inf/NaN.
+__device__ __forceinline__ void half_split(float v, __half& hi, __half& lo) {
+    unsigned short h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    hi = __ushort_as_half(h);
+    lo = __float2half_rn(v - __half2float(hi));
 }
-__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
-    hi = tf32_rna(v);
-    lo = tf32_rna(v - hi);
+// four consecutive values -> 8-byte stores into the hi / lo planes
+__device__ __forceinline__ void half_split_store4(__half* hi_p, __half* lo_p, float4 v) {
+    __half h[4], l[4];
+    half_split(v.x, h[0], l[0]); half_split(v.y, h[1], l[1]);
+    half_split(v.z, h[2], l[2]); half_split(v.w, h[3], l[3]);
+    uint2 uh, ul;
+    uh.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+    uh.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    ul.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+    ul.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+    *reinterpret_cast<uint2*>(hi_p) = uh;
+    *reinterpret_cast<uint2*>(lo_p) = ul;
+}
+// four consecutive values of hi + lo (un-scaled by the caller)
+__device__ __forceinline__ float4 half_pair_load4(const __half* hi_p, const __half* lo_p) {
+    const uint2 uh = __ldg(reinterpret_cast<const uint2*>(hi_p));
+    const uint2 ul = __ldg(reinterpret_cast<const uint2*>(lo_p));
+    const __half2 h0 = *reinterpret_cast<const __half2*>(&uh.x), h1 = *reinterpret_cast<const __half2*>(&uh.y);
+    const __half2 l0 = *reinterpret_cast<const __half2*>(&ul.x), l1 = *reinterpret_cast<const __half2*>(&ul.y);
+    const float2 a = __half22float2(h0), b = __half22float2(h1), c = __half22float2(l0), d = __half22float2(l1);
+    return make_float4(a.x + c.x, a.y + c.y, b.x + d.x, b.y + d.y);
 }
 
 }  // namespace tip

@@ -36,11 +36,11 @@ __global__ void condition_kernel(const float* __restrict__ x_imu, const float* _
             if (keep_mask != nullptr) v *= keep_mask[(int64_t)r * size_s + cs] * past_scale;
             else if (p_past > 0.f) v *= dropout_factor(p_past, inv_past, seed ^ 0x2222, i);   // :77
         }
-        if (out_lo != nullptr) {
-            float hi, lo;
-            tf32_split(v, hi, lo);
-            out[i] = hi;
-            out_lo[i] = lo;
+        if (out_lo != nullptr) {          // FP16 hi/lo planes (scale 1: raw model input) for the tcgen05 engine
+            __half hi, lo;
+            half_split(v, hi, lo);
+            reinterpret_cast<__half*>(out)[i] = hi;
+            reinterpret_cast<__half*>(out_lo)[i] = lo;
         } else {
             out[i] = v;
         }
@@ -51,17 +51,20 @@ __global__ void condition_kernel(const float* __restrict__ x_imu, const float* _
 // C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  A and W are K-contiguous (nn.Linear layout).
 struct Epi {
     const float* bias;      // [N]
-    const float* resid;     // LN variant: residual rows [M][ldr] (fp32, or hi plane when resid_lo)
-    const float* resid_lo;  // optional lo plane of the residual
+    const float* resid;     // LN variant: residual rows [M][ldr]: fp32, or (resid_lo != null) the __half hi plane
+    const float* resid_lo;  // __half lo plane of the residual (planes hold ACT_SCALE * x)
     int ldr;
     const float* gamma;     // LN affine
     const float* beta;
-    float* out;             // fp32 output, or hi plane when out_lo != nullptr
-    float* out_lo;
+    float* out;             // fp32 output, or (out_lo != null) the __half hi plane of ACT_SCALE * output
+    float* out_lo;          // __half lo plane
+    const float* acc_scale; // tcgen05 engine: device scalar multiplying the accumulator (1/(s_a*s_w))
     int ldc;
     int relu;
     float drop_p;           // dropout on the GEMM output (after ReLU; before the residual add)
     uint64_t seed;
+    int dbg;                // experiment flags (TIP_DBG env): 1 skip stores, 2 skip bias loads
+    unsigned long long* tbuf;   // optional phase timestamps of CTA 0 (TIP_DBG & 4)
 };
 
 constexpr int SG_BK = 16;
@@ -190,7 +193,6 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
                 float r = 0.f;
                 if (row_ok) {
                     r = ep.resid[(size_t)row * ep.ldr + col];
-                    if (ep.resid_lo) r += ep.resid_lo[(size_t)row * ep.ldr + col];
                 }
                 v[j] += r;
                 s += v[j];
@@ -216,31 +218,11 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
                 const int col = n0 + g * (BN / 2) + tx * 4;
                 float* o = ep.out + (size_t)row * ep.ldc + col;
                 if (col + 3 < N && (ep.ldc & 3) == 0) {
-                    if (ep.out_lo) {
-                        float4 hi, lo;
-                        tf32_split(v[g * 4 + 0], hi.x, lo.x);
-                        tf32_split(v[g * 4 + 1], hi.y, lo.y);
-                        tf32_split(v[g * 4 + 2], hi.z, lo.z);
-                        tf32_split(v[g * 4 + 3], hi.w, lo.w);
-                        *reinterpret_cast<float4*>(o) = hi;
-                        *reinterpret_cast<float4*>(ep.out_lo + (size_t)row * ep.ldc + col) = lo;
-                    } else {
-                        *reinterpret_cast<float4*>(o) =
-                            make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-                    }
+                    *reinterpret_cast<float4*>(o) = make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (col + j < N) {
-                            if (ep.out_lo) {
-                                float hi, lo;
-                                tf32_split(v[g * 4 + j], hi, lo);
-                                o[j] = hi;
-                                ep.out_lo[(size_t)row * ep.ldc + col + j] = lo;
-                            } else {
-                                o[j] = v[g * 4 + j];
-                            }
-                        }
+                        if (col + j < N) o[j] = v[g * 4 + j];
                 }
             }
         }
@@ -250,30 +232,34 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // Causal multi-head self-attention core (reference :85-91 -> nn.MultiheadAttention):
 //   P = softmax(q k^T + causal mask) [dropout], o = P v, per (window b, head h); 1/sqrt(d) is folded
-//   into W_q at pack time.  One thread owns the query-row pair (p, L-1-p) so every lane does the
-//   same ~L+1 keys of causal work; KS lanes split the keys of a pair and merge (max, sum, o) with
-//   warp shuffles.  K and V of the block's heads are staged once in shared memory and read as
-//   128-bit broadcasts.  The contraction is tiny (d=16, L<=40): FFMA, no tensor cores.
+//   into W_q at pack time.  The contraction is tiny (d=16, L<=40): FFMA + warp shuffles, no tensor
+//   cores; the kernel is bound by moving qkv in and o out, so both go through shared memory in
+//   512-byte-per-row coalesced pieces (HPB=8 heads of one window per CTA).
+//   One thread group of KS lanes owns the query-row pair (p, L-1-p), so every group does the same
+//   L+1 keys of causal work; the KS lanes split the keys and merge (max, sum, o) with shuffles.
+//   Two passes over the keys (max, then exp/accumulate) keep everything in registers.
 template <int KS, int HPB>
 __global__ void __launch_bounds__(HPB * 20 * KS)
 attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ out_lo,
                  int L, float drop_p, uint64_t seed) {
-    constexpr int NJ = (MAXL + KS - 1) / KS;
-    __shared__ __align__(16) float Ks[HPB][MAXL][HD];
-    __shared__ __align__(16) float Vs[HPB][MAXL][HD];
+    constexpr int NT = HPB * 20 * KS;
+    __shared__ __align__(16) float Qs[MAXL][HPB][HD];      // reused for the output tile
+    __shared__ __align__(16) float Ks[MAXL][HPB][HD];
+    __shared__ __align__(16) float Vs[MAXL][HPB][HD];
     const int b = blockIdx.x;
     const int h0 = blockIdx.y * HPB;
     const int tid = threadIdx.x;
-    const float* base = qkv + (size_t)b * L * (3 * E);
+    const float* base = qkv + (size_t)b * L * (3 * E) + h0 * HD;
 
-    // stage K, V: HPB heads x L rows x 16 floats (4 float4 per row)
-    for (int i = tid; i < HPB * L * 4; i += blockDim.x) {
-        const int hl = i / (L * 4);
-        const int rem = i - hl * (L * 4);
-        const int row = rem >> 2, q4 = rem & 3;
-        const float* src = base + (size_t)row * (3 * E) + (h0 + hl) * HD + q4 * 4;
-        *reinterpret_cast<float4*>(&Ks[hl][row][q4 * 4]) = __ldg(reinterpret_cast<const float4*>(src + E));
-        *reinterpret_cast<float4*>(&Vs[hl][row][q4 * 4]) = __ldg(reinterpret_cast<const float4*>(src + 2 * E));
+    // stage Q, K, V of HPB heads: per row 3 pieces of HPB*16 contiguous floats
+    constexpr int F4_ROW = HPB * HD / 4;
+    for (int i = tid; i < L * 3 * F4_ROW; i += NT) {
+        const int row = i / (3 * F4_ROW);
+        const int rem = i - row * (3 * F4_ROW);
+        const int which = rem / F4_ROW, c4 = rem - which * F4_ROW;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * (3 * E) + which * E) + c4);
+        float* dst = which == 0 ? &Qs[row][0][0] : (which == 1 ? &Ks[row][0][0] : &Vs[row][0][0]);
+        reinterpret_cast<float4*>(dst)[c4] = v;
     }
     __syncthreads();
 
@@ -287,70 +273,66 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* 
     const bool two = active && (ra != rb);
 
     float qa[HD], qb[HD];
-    {
-        const float* qpa = base + (size_t)ra * (3 * E) + (h0 + hl) * HD;
-        const float* qpb = base + (size_t)rb * (3 * E) + (h0 + hl) * HD;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 va = *reinterpret_cast<const float4*>(&Qs[ra][hl][i * 4]);
+        const float4 vb = *reinterpret_cast<const float4*>(&Qs[rb][hl][i * 4]);
+        qa[i * 4 + 0] = va.x; qa[i * 4 + 1] = va.y; qa[i * 4 + 2] = va.z; qa[i * 4 + 3] = va.w;
+        qb[i * 4 + 0] = vb.x; qb[i * 4 + 1] = vb.y; qb[i * 4 + 2] = vb.z; qb[i * 4 + 3] = vb.w;
+    }
+    const int jend = active ? rb : -1;
+    // pass 1: row maxima
+    float ma = -INFINITY, mb = -INFINITY;
+    for (int j = ks; j <= jend; j += KS) {
+        float da = 0.f, db = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float4 va = __ldg(reinterpret_cast<const float4*>(qpa) + i);
-            const float4 vb = __ldg(reinterpret_cast<const float4*>(qpb) + i);
-            qa[i * 4 + 0] = va.x; qa[i * 4 + 1] = va.y; qa[i * 4 + 2] = va.z; qa[i * 4 + 3] = va.w;
-            qb[i * 4 + 0] = vb.x; qb[i * 4 + 1] = vb.y; qb[i * 4 + 2] = vb.z; qb[i * 4 + 3] = vb.w;
+            const float4 kv = *reinterpret_cast<const float4*>(&Ks[j][hl][i * 4]);
+            da = fmaf(qa[i * 4 + 0], kv.x, da); db = fmaf(qb[i * 4 + 0], kv.x, db);
+            da = fmaf(qa[i * 4 + 1], kv.y, da); db = fmaf(qb[i * 4 + 1], kv.y, db);
+            da = fmaf(qa[i * 4 + 2], kv.z, da); db = fmaf(qb[i * 4 + 2], kv.z, db);
+            da = fmaf(qa[i * 4 + 3], kv.w, da); db = fmaf(qb[i * 4 + 3], kv.w, db);
         }
-    }
-    float sa[NJ], sb[NJ];
-    float ma = -INFINITY, mb = -INFINITY;
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-        const int j = jj * KS + ks;
-        sa[jj] = -INFINITY;
-        sb[jj] = -INFINITY;
-        if (active && j <= rb) {
-            float da = 0.f, db = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 kv = *reinterpret_cast<const float4*>(&Ks[hl][j][i * 4]);
-                da = fmaf(qa[i * 4 + 0], kv.x, da); db = fmaf(qb[i * 4 + 0], kv.x, db);
-                da = fmaf(qa[i * 4 + 1], kv.y, da); db = fmaf(qb[i * 4 + 1], kv.y, db);
-                da = fmaf(qa[i * 4 + 2], kv.z, da); db = fmaf(qb[i * 4 + 2], kv.z, db);
-                da = fmaf(qa[i * 4 + 3], kv.w, da); db = fmaf(qb[i * 4 + 3], kv.w, db);
-            }
-            sb[jj] = db;
-            mb = fmaxf(mb, db);
-            if (j <= ra) { sa[jj] = da; ma = fmaxf(ma, da); }
-        }
+        mb = fmaxf(mb, db);
+        if (j <= ra) ma = fmaxf(ma, da);
     }
 #pragma unroll
     for (int o = KS >> 1; o > 0; o >>= 1) {
         ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
         mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
     }
+    // pass 2: exp, row sums, P v
     float oa[HD], ob[HD], la = 0.f, lb = 0.f;
 #pragma unroll
     for (int i = 0; i < HD; ++i) { oa[i] = 0.f; ob[i] = 0.f; }
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    for (int j = ks; j <= jend; j += KS) {
+        float da = 0.f, db = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-        const int j = jj * KS + ks;
-        if (active && j <= rb) {
-            float pa = (j <= ra) ? expf(sa[jj] - ma) : 0.f;
-            float pb = expf(sb[jj] - mb);
-            la += pa;
-            lb += pb;
-            if (drop_p > 0.f) {   // attention-probability dropout (train mode only)
-                const uint64_t ida = (((uint64_t)b * NH + h0 + hl) * MAXL + ra) * MAXL + j;
-                const uint64_t idb = (((uint64_t)b * NH + h0 + hl) * MAXL + rb) * MAXL + j;
-                pa *= dropout_factor(drop_p, inv_keep, seed, ida);
-                pb *= dropout_factor(drop_p, inv_keep, seed, idb);
-            }
+        for (int i = 0; i < 4; ++i) {
+            const float4 kv = *reinterpret_cast<const float4*>(&Ks[j][hl][i * 4]);
+            da = fmaf(qa[i * 4 + 0], kv.x, da); db = fmaf(qb[i * 4 + 0], kv.x, db);
+            da = fmaf(qa[i * 4 + 1], kv.y, da); db = fmaf(qb[i * 4 + 1], kv.y, db);
+            da = fmaf(qa[i * 4 + 2], kv.z, da); db = fmaf(qb[i * 4 + 2], kv.z, db);
+            da = fmaf(qa[i * 4 + 3], kv.w, da); db = fmaf(qb[i * 4 + 3], kv.w, db);
+        }
+        float pa = (j <= ra) ? expf(da - ma) : 0.f;
+        float pb = expf(db - mb);
+        la += pa;
+        lb += pb;
+        if (drop_p > 0.f) {   // attention-probability dropout (train mode only)
+            const uint64_t ida = (((uint64_t)b * NH + h0 + hl) * MAXL + ra) * MAXL + j;
+            const uint64_t idb = (((uint64_t)b * NH + h0 + hl) * MAXL + rb) * MAXL + j;
+            pa *= dropout_factor(drop_p, inv_keep, seed, ida);
+            pb *= dropout_factor(drop_p, inv_keep, seed, idb);
+        }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 vv = *reinterpret_cast<const float4*>(&Vs[hl][j][i * 4]);
-                oa[i * 4 + 0] = fmaf(pa, vv.x, oa[i * 4 + 0]); ob[i * 4 + 0] = fmaf(pb, vv.x, ob[i * 4 + 0]);
-                oa[i * 4 + 1] = fmaf(pa, vv.y, oa[i * 4 + 1]); ob[i * 4 + 1] = fmaf(pb, vv.y, ob[i * 4 + 1]);
-                oa[i * 4 + 2] = fmaf(pa, vv.z, oa[i * 4 + 2]); ob[i * 4 + 2] = fmaf(pb, vv.z, ob[i * 4 + 2]);
-                oa[i * 4 + 3] = fmaf(pa, vv.w, oa[i * 4 + 3]); ob[i * 4 + 3] = fmaf(pb, vv.w, ob[i * 4 + 3]);
-            }
+        for (int i = 0; i < 4; ++i) {
+            const float4 vv = *reinterpret_cast<const float4*>(&Vs[j][hl][i * 4]);
+            oa[i * 4 + 0] = fmaf(pa, vv.x, oa[i * 4 + 0]); ob[i * 4 + 0] = fmaf(pb, vv.x, ob[i * 4 + 0]);
+            oa[i * 4 + 1] = fmaf(pa, vv.y, oa[i * 4 + 1]); ob[i * 4 + 1] = fmaf(pb, vv.y, ob[i * 4 + 1]);
+            oa[i * 4 + 2] = fmaf(pa, vv.z, oa[i * 4 + 2]); ob[i * 4 + 2] = fmaf(pb, vv.z, ob[i * 4 + 2]);
+            oa[i * 4 + 3] = fmaf(pa, vv.w, oa[i * 4 + 3]); ob[i * 4 + 3] = fmaf(pb, vv.w, ob[i * 4 + 3]);
         }
     }
 #pragma unroll
@@ -363,29 +345,32 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* 
             ob[i] += __shfl_xor_sync(0xffffffffu, ob[i], o);
         }
     }
+    // normalised rows -> the Q tile (each row of Qs is read and written by its own lane group only)
     if (active && ks == 0) {
         const float ia = 1.f / la, ib = 1.f / lb;
-        float* da = out + ((size_t)b * L + ra) * E + (h0 + hl) * HD;
-        float* db = out + ((size_t)b * L + rb) * E + (h0 + hl) * HD;
-        float* dal = out_lo ? out_lo + ((size_t)b * L + ra) * E + (h0 + hl) * HD : nullptr;
-        float* dbl = out_lo ? out_lo + ((size_t)b * L + rb) * E + (h0 + hl) * HD : nullptr;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float4 va = make_float4(oa[i * 4 + 0] * ia, oa[i * 4 + 1] * ia, oa[i * 4 + 2] * ia, oa[i * 4 + 3] * ia);
-            float4 vb = make_float4(ob[i * 4 + 0] * ib, ob[i * 4 + 1] * ib, ob[i * 4 + 2] * ib, ob[i * 4 + 3] * ib);
-            if (out_lo) {
-                float4 ha, lla, hb, llb;
-                tf32_split(va.x, ha.x, lla.x); tf32_split(va.y, ha.y, lla.y);
-                tf32_split(va.z, ha.z, lla.z); tf32_split(va.w, ha.w, lla.w);
-                tf32_split(vb.x, hb.x, llb.x); tf32_split(vb.y, hb.y, llb.y);
-                tf32_split(vb.z, hb.z, llb.z); tf32_split(vb.w, hb.w, llb.w);
-                reinterpret_cast<float4*>(da)[i] = ha;
-                reinterpret_cast<float4*>(dal)[i] = lla;
-                if (two) { reinterpret_cast<float4*>(db)[i] = hb; reinterpret_cast<float4*>(dbl)[i] = llb; }
-            } else {
-                reinterpret_cast<float4*>(da)[i] = va;
-                if (two) reinterpret_cast<float4*>(db)[i] = vb;
-            }
+            *reinterpret_cast<float4*>(&Qs[ra][hl][i * 4]) =
+                make_float4(oa[i * 4 + 0] * ia, oa[i * 4 + 1] * ia, oa[i * 4 + 2] * ia, oa[i * 4 + 3] * ia);
+            if (two)
+                *reinterpret_cast<float4*>(&Qs[rb][hl][i * 4]) =
+                    make_float4(ob[i * 4 + 0] * ib, ob[i * 4 + 1] * ib, ob[i * 4 + 2] * ib, ob[i * 4 + 3] * ib);
+        }
+    }
+    __syncthreads();
+    // coalesced store (fp32, or FP16 hi/lo planes of ACT_SCALE*o for the tcgen05 out-projection)
+    float* ob_ = out + (size_t)b * L * E + h0 * HD;
+    __half* oh_ = reinterpret_cast<__half*>(out) + (size_t)b * L * E + h0 * HD;
+    __half* ol_ = out_lo ? reinterpret_cast<__half*>(out_lo) + (size_t)b * L * E + h0 * HD : nullptr;
+    for (int i = tid; i < L * F4_ROW; i += NT) {
+        const int row = i / F4_ROW, c4 = i - row * F4_ROW;
+        const float4 v = reinterpret_cast<const float4*>(&Qs[row][0][0])[c4];
+        if (ol_) {
+            const size_t e = (size_t)row * E + c4 * 4;
+            half_split_store4(oh_ + e, ol_ + e,
+                              make_float4(v.x * ACT_SCALE, v.y * ACT_SCALE, v.z * ACT_SCALE, v.w * ACT_SCALE));
+        } else {
+            reinterpret_cast<float4*>(ob_ + (size_t)row * E)[c4] = v;
         }
     }
 }
@@ -436,16 +421,211 @@ rnn_stream_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t,
             if (b0 + r < B) {
                 const size_t o = ((size_t)(b0 + r) * L + t) * R + n;
                 if (hs_lo) {
-                    float hi, lo;
-                    tf32_split(v, hi, lo);
-                    hs[o] = hi;
-                    hs_lo[o] = lo;
+                    __half hi, lo;
+                    half_split(v * ACT_SCALE, hi, lo);
+                    reinterpret_cast<__half*>(hs)[o] = hi;
+                    reinterpret_cast<__half*>(hs_lo)[o] = lo;
                 } else {
                     hs[o] = v;
                 }
             }
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tanh RNN recurrence, cluster version (the production kernel).  The recurrence is the only serial
+// chain of the path (40 dependent 512x512 mat-vecs per window), so the 1 MB W_hh must not be
+// re-streamed from L2 every step: a thread-block cluster of 8 CTAs keeps W_hh resident IN REGISTERS
+// (CTA c owns hidden units [64c, 64c+64); thread (u, kq) holds the 128 weights of row u for the
+// k-slices kq and kq+4), the hidden state lives in every CTA's shared memory as 8 slices of 64
+// units, and after each step a CTA pushes its slice to the 7 peers with one asynchronous bulk
+// DSMEM copy each (cp.async.bulk.shared::cluster, 2 KB), completion counted on an mbarrier in the
+// destination CTA -- no cluster-wide barrier inside the time loop.  A cluster carries up to 16
+// windows at once as two groups of 8: while group A's slices are in flight the cluster computes
+// group B (windows are independent chains), which hides the exchange latency.  FFMA fp32
+// throughout (parity with the reference's fp32 RNN).
+constexpr int RC_CTAS = 8;                       // CTAs per cluster
+constexpr int RC_UNITS = R / RC_CTAS;            // 64 hidden units per CTA
+constexpr int RC_GROUP = 8;                      // windows per group
+constexpr int RC_ROWS = 2 * RC_GROUP;            // windows per cluster pass
+constexpr int RC_RPITCH = 72;                    // floats per (slice, window): 2 x (32 + 4 pad)
+constexpr int RC_SLICE = RC_ROWS * RC_RPITCH + 8; // floats per CTA-slice (+32 B: bank spread)
+constexpr int RC_BUF = RC_CTAS * RC_SLICE;       // floats per h buffer
+constexpr int RC_GROUP_BYTES = RC_GROUP * RC_RPITCH * (int)sizeof(float);     // 2304 B per push
+constexpr int RC_SMEM_BYTES = 2 * RC_BUF * (int)sizeof(float) + 64;
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dsmem_bulk_push(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
+}
+__device__ __forceinline__ void rc_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rc_mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rc_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    unsigned long long t0 = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000ull) __trap();        // protocol bug: fail loudly, never hang
+    }
+}
+
+// 32 partial sums per lane, 16 lanes (lane & 15) hold different k-slices: butterfly with halving.
+// Afterwards lane l holds the two complete sums with index 2*(l&15) and 2*(l&15)+1.
+__device__ __forceinline__ void rc_reduce16(const float (&v)[32], int lane, float& o0, float& o1) {
+    float a[16], b[8], c[4];
+    const bool u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float send = u8 ? v[i] : v[i + 16];
+        a[i] = (u8 ? v[i + 16] : v[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = u4 ? a[i] : a[i + 8];
+        b[i] = (u4 ? a[i + 8] : a[i]) + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = u2 ? b[i] : b[i + 4];
+        c[i] = (u2 ? b[i + 4] : b[i]) + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    {
+        const float s0 = u1 ? c[0] : c[2], s1 = u1 ? c[1] : c[3];
+        o0 = (u1 ? c[2] : c[0]) + __shfl_xor_sync(0xffffffffu, s0, 1);
+        o1 = (u1 ? c[3] : c[1]) + __shfl_xor_sync(0xffffffffu, s1, 1);
+    }
+}
+
+// Thread (ug, s): unit group ug = tid/16 (4 hidden units), k-slice s = tid%16 (32 k).  Its 128 weights
+// stay in registers for the whole launch; per k-chunk of 4 it loads one float4 of h per window and
+// issues 16 FMAs with it (4 units), so shared-memory bandwidth (a 128-bit load costs 4 crossbar
+// cycles) and the FMA pipes are balanced.
+__global__ void __cluster_dims__(RC_CTAS, 1, 1) __launch_bounds__(256, 1)
+rnn_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh,
+                   float* __restrict__ hs, float* __restrict__ hs_lo, int B, int L) {
+    extern __shared__ __align__(128) float hbuf[];          // [2 buffers][8 slices][16 windows][72] (+pad)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ug = tid >> 4, s = tid & 15;
+    const uint32_t rank = cluster_ctarank();
+    const int unit0 = (int)rank * RC_UNITS + ug * 4;         // first of this thread's 4 units
+    const int n_clusters = gridDim.x / RC_CTAS, cluster_id = blockIdx.x / RC_CTAS;
+    const uint32_t hbuf_s = (uint32_t)__cvta_generic_to_shared(hbuf);
+    const uint32_t bar_s = hbuf_s + 2u * RC_BUF * 4u;        // 4 mbarriers: [group][buffer]
+
+    float w[4][32];                                          // W_hh[unit0 + u][32 s + kk]
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float4* wp = reinterpret_cast<const float4*>(whh + (size_t)(unit0 + u) * R + s * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(wp + j);
+            w[u][4 * j] = t.x; w[u][4 * j + 1] = t.y; w[u][4 * j + 2] = t.z; w[u][4 * j + 3] = t.w;
+        }
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) rc_mbar_init(bar_s + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_arrive();
+    cluster_wait();
+    uint32_t fills = 0;                                      // bit (g*2+p): parity of the next fill to wait for
+
+    // after the reduction this lane owns window fr (of the group) and units fu, fu+1 (of the CTA)
+    const int fr = (lane & 15) >> 1;
+    const int fu = ug * 4 + 2 * (lane & 1);
+    // k position 64*rank + fu inside a window's h row -> slice `rank`, half fu/32, offset fu%32
+    const int h_local = (fu >> 5) * 36 + (fu & 31);
+    // where this thread reads h: k-slice s lives in CTA-slice s/2, half s%2
+    const int h_read = (s >> 1) * RC_SLICE + (s & 1) * 36;
+
+    for (int rb = cluster_id; rb * RC_ROWS < B; rb += n_clusters) {
+        const int b0 = rb * RC_ROWS;
+        const int nrows = min(RC_ROWS, B - b0);
+        const int ngroups = nrows > RC_GROUP ? 2 : 1;        // uniform over the cluster
+        for (int t = 0; t < L; ++t) {
+            const int cur = t & 1, nxt = cur ^ 1;
+            for (int g = 0; g < ngroups; ++g) {
+                const int nr = min(RC_GROUP, nrows - g * RC_GROUP);
+                // arm the barrier that will collect the peers' h_g(t) (its previous fill, h_g(t-2), was
+                // consumed during step t-1; early complete_tx from fast peers is legal)
+                if (tid == 0 && t + 1 < L) rc_mbar_expect(bar_s + 8u * (g * 2 + nxt), (RC_CTAS - 1) * RC_GROUP_BYTES);
+                const int wrow = g * RC_GROUP + fr;          // window (within the block) this lane finishes
+                float2 giv = make_float2(0.f, 0.f);
+                if (fr < nr) giv = __ldg(reinterpret_cast<const float2*>(gi + ((size_t)(b0 + wrow) * L + t) * R + rank * RC_UNITS + fu));
+                float o0 = 0.f, o1 = 0.f;
+                if (t > 0) {
+                    // h_g(t-1): 7 peer slices (mbarrier) + the local slice (the __syncthreads below)
+                    const int bi = g * 2 + cur;
+                    rc_mbar_wait(bar_s + 8u * bi, (fills >> bi) & 1u);
+                    fills ^= 1u << bi;
+                    float acc[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+                    const float* hb = hbuf + cur * RC_BUF + h_read + (g * RC_GROUP) * RC_RPITCH;
+#pragma unroll
+                    for (int kc = 0; kc < 8; ++kc) {
+#pragma unroll
+                        for (int r = 0; r < RC_GROUP; ++r) {
+                            const float4 hv = *reinterpret_cast<const float4*>(hb + r * RC_RPITCH + 4 * kc);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                float a = acc[r * 4 + u];
+                                a = fmaf(w[u][4 * kc], hv.x, a);
+                                a = fmaf(w[u][4 * kc + 1], hv.y, a);
+                                a = fmaf(w[u][4 * kc + 2], hv.z, a);
+                                a = fmaf(w[u][4 * kc + 3], hv.w, a);
+                                acc[r * 4 + u] = a;
+                            }
+                        }
+                    }
+                    rc_reduce16(acc, lane, o0, o1);          // -> window fr, units fu, fu+1
+                }
+                const float va = tanhf(o0 + giv.x), vb = tanhf(o1 + giv.y);
+                float* mine = hbuf + nxt * RC_BUF + (int)rank * RC_SLICE + wrow * RC_RPITCH + h_local;
+                mine[0] = va;                                // windows beyond nr carry don't-care values
+                mine[1] = vb;
+                if (fr < nr) {
+                    const size_t o = ((size_t)(b0 + wrow) * L + t) * R + rank * RC_UNITS + fu;
+                    if (hs_lo) {
+                        __half h0, l0, h1, l1;
+                        half_split(va * ACT_SCALE, h0, l0); half_split(vb * ACT_SCALE, h1, l1);
+                        *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(hs) + o) = __halves2half2(h0, h1);
+                        *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(hs_lo) + o) = __halves2half2(l0, l1);
+                    } else {
+                        *reinterpret_cast<float2*>(hs + o) = make_float2(va, vb);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
+                __syncthreads();
+                if (t + 1 < L && tid < RC_CTAS && (uint32_t)tid != rank) {
+                    const uint32_t off = (uint32_t)(nxt * RC_BUF + (int)rank * RC_SLICE + (g * RC_GROUP) * RC_RPITCH) * 4u;
+                    dsmem_bulk_push(map_to_cta(hbuf_s + off, (uint32_t)tid), hbuf_s + off, RC_GROUP_BYTES,
+                                    map_to_cta(bar_s + 8u * (g * 2 + nxt), (uint32_t)tid));
+                }
+            }
+        }
+        // next row block reuses the buffers: everyone must be done reading first
+        cluster_arrive();
+        cluster_wait();
     }
 }
 
@@ -543,12 +723,33 @@ __global__ void pack_pad_rows_kernel(const float* __restrict__ src, float* __res
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows_pad * cols) dst[i] = (i / cols < rows) ? src[i] : 0.f;
 }
-__global__ void pack_split_kernel(const float* __restrict__ src, float* __restrict__ hi,
-                                  float* __restrict__ lo, int64_t n) {
+// max |w| of a matrix -> power-of-two scale s_w with s_w * max|w| in [16384, 32768); writes
+// scales[idx] = 1 / (s_w * act_scale) for the GEMM epilogue and scales_w[idx] = s_w for the split.
+__global__ void pack_scale_kernel(const float* __restrict__ src, int64_t n, float act_scale,
+                                  float* __restrict__ inv_scale, float* __restrict__ w_scale) {
+    __shared__ float red[256];
+    float m = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += 256) m = fmaxf(m, fabsf(src[i]));
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float mx = red[0];
+        float sw = 1.f;
+        if (mx > 0.f && mx < INFINITY) sw = exp2f(floorf(log2f(32768.f / mx)));
+        *w_scale = sw;
+        *inv_scale = 1.f / (sw * act_scale);
+    }
+}
+__global__ void pack_split_kernel(const float* __restrict__ src, __half* __restrict__ hi,
+                                  __half* __restrict__ lo, int64_t n, const float* __restrict__ w_scale) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        float h, l;
-        tf32_split(src[i], h, l);
+        __half h, l;
+        half_split(src[i] * *w_scale, h, l);
         hi[i] = h;
         lo[i] = l;
     }

@@ -1,18 +1,20 @@
 // tcgen05 GEMM engine of the TIP hot path (sm_100a): C[M,N] = A[M,K] * W[N,K]^T with fp32-parity
-// accuracy from three TF32 tensor-core products per tile (error-compensated split,
-// a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with hi = rna_tf32(x), lo = rna_tf32(x - hi); a single
-// TF32 pass misses the 1e-4 parity bar by 100x).
+// accuracy from three FP16 tensor-core products per tile (error-compensated split,
+// a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with hi = fp16(s*x), lo = fp16(s*x - hi), s a power of
+// two keeping the operands in fp16's normal range; 22 significant bits like a 3xTF32 split, but at
+// the f16 MMA rate and half the operand bytes.  A single TF32/BF16 pass misses the 1e-4 parity bar
+// by 100x).  Accumulation is fp32 in TMEM; the epilogue un-scales exactly.
 //
 // Persistent, warp-specialised kernel, one CTA per SM:
 //   warp 0      TMA producer   : cp.async.bulk.tensor 2D tiles (128B-swizzled, K-major) of the four
 //                                operand planes into a multi-stage shared-memory ring (mbarrier
 //                                complete_tx)
-//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8),
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16),
 //                                3 per k-step, accumulating in TMEM; tcgen05.commit frees the smem
 //                                stage / publishes the accumulator
 //   warps 2..5  epilogue       : tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next
 //                                tile's MMAs overlap), fused bias / ReLU / dropout, or residual +
-//                                LayerNorm over the full 256-wide row, optional TF32 hi/lo split of
+//                                LayerNorm over the full 256-wide row, optional FP16 hi/lo split of
 //                                the output for the next GEMM, coalesced-by-row global stores.
 #pragma once
 #include <cuda.h>
@@ -26,8 +28,7 @@ enum UmmaGemmId { UG_IN = 0, UG_QKV, UG_OUT, UG_FF1, UG_FF2, UG_IH, UG_HEAD_R, U
 constexpr bool UMMA_AVAILABLE = true;
 
 constexpr int UM_BM = 128;          // UMMA M (cta_group::1)
-constexpr int UM_BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int UM_THREADS = 192;
+constexpr int UM_BK = 64;           // fp16 elements per k-block = one 128-byte swizzle row
 
 template <int BN> struct UmmaCfg {
     static constexpr int STAGES = (BN == 256) ? 2 : 3;
@@ -35,7 +36,8 @@ template <int BN> struct UmmaCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
     static constexpr int TMEM_COLS = 2 * BN;                    // double-buffered accumulator
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * 4096 /*epilogue staging*/ + 1024 /*align slack*/ +
+                                      128 /*barriers*/ + 1024 /*LN row stats*/;
 };
 
 namespace ptx {
@@ -89,11 +91,11 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -141,11 +143,57 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// kind::tf32 instruction descriptor: D fp32 (bits 4-5 = 1), A/B TF32 (format 2 at bits 7-9 / 10-12),
+// kind::f16 instruction descriptor: D fp32 (bits 4-5 = 1), A/B FP16 (format 0 at bits 7-9 / 10-12),
 // both K-major, N>>3 at bit 17, M>>4 at bit 24.
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// ---- epilogue helpers ----------------------------------------------------------------------------
+// Each epilogue warp owns a 32-row x 32-column fp32 staging tile in shared memory (4 KB, 16-byte
+// chunks XOR-swizzled by row so both access patterns below are bank-conflict free):
+//   "row" pattern   : thread t <-> row t, all 8 chunks (how tcgen05.ld delivers the accumulator)
+//   "coal" pattern  : lane l <-> chunk l%8 of rows i*4 + l/8, i = 0..7 (4 full 128-byte lines per
+//                     warp instruction in global memory)
+__device__ __forceinline__ float4* stg_ptr(float* stg, int row, int chunk) {
+    return reinterpret_cast<float4*>(stg) + row * 8 + (chunk ^ (row & 7));
+}
+__device__ __forceinline__ void stg_write_row(float* stg, int lane, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *stg_ptr(stg, lane, j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void stg_read_row(const float* stg, int lane, float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 t = *stg_ptr(const_cast<float*>(stg), lane, j);
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+}
+// fp32 output, or (ol != null) FP16 hi/lo planes of ACT_SCALE * x
+__device__ __forceinline__ void store4(float* o, float* ol, size_t off, int ncols_left, bool vec_ok, float4 x) {
+    if (ol) {
+        __half* oh = reinterpret_cast<__half*>(o) + off;
+        __half* olh = reinterpret_cast<__half*>(ol) + off;
+        if (vec_ok && ncols_left >= 4) {
+            half_split_store4(oh, olh, make_float4(x.x * ACT_SCALE, x.y * ACT_SCALE, x.z * ACT_SCALE, x.w * ACT_SCALE));
+        } else {
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < ncols_left) { __half hi, lo; half_split(xs[q] * ACT_SCALE, hi, lo); oh[q] = hi; olh[q] = lo; }
+        }
+    } else if (vec_ok && ncols_left >= 4) {
+        *reinterpret_cast<float4*>(o + off) = x;
+    } else {
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q < ncols_left) o[off + q] = xs[q];
+    }
+}
+
+constexpr int UM_EPI_WARPS = 8;                 // two warps per TMEM lane quarter (column halves)
+constexpr int UM_THREADS = 64 + 32 * UM_EPI_WARPS;
 
 template <int BN, bool LN>
 __global__ void __launch_bounds__(UM_THREADS, 1)
@@ -154,14 +202,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                  int M, int N, int K, Epi ep) {
     using Cfg = UmmaCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    // 128B-swizzled operand tiles need 1024-byte alignment.  The kernel has no static shared memory,
+    // so the dynamic window starts at shared offset 0; keeping the pointer un-cast preserves the
+    // shared address space (LDS/STS instead of generic LD/ST for the epilogue staging).
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
+    float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);          // 8 x 4 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + UM_EPI_WARPS * 4096);
     uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
     uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
     uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]       MMA -> epilogue
     uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* row_stat = reinterpret_cast<float*>(bars + 2 * STAGES + 6);   // LN: [2 halves][128 rows] partials, then mean/rstd
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (N + BN - 1) / BN;
@@ -173,7 +226,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         ptx::prefetch_tmap(&mapA_hi); ptx::prefetch_tmap(&mapA_lo);
         ptx::prefetch_tmap(&mapB_hi); ptx::prefetch_tmap(&mapB_lo);
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], UM_EPI_WARPS); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -181,6 +234,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+#define TIP_TS(i) do { if (ep.tbuf && blockIdx.x == 0 && lane == 0) ep.tbuf[i] = ptx::globaltimer_ns(); } while (0)
+    if (warp == 2) TIP_TS(0);
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -203,7 +258,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(UM_BM, BN);
+            constexpr uint32_t idesc = umma_idesc_f16(UM_BM, BN);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -214,150 +269,178 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
+                    if (kb == 0 && it == 0) TIP_TS(1);
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint64_t a_hi = umma_smem_desc(sa), a_lo = umma_smem_desc(sa + Cfg::A_BYTES);
                     const uint64_t b_hi = umma_smem_desc(sa + 2 * Cfg::A_BYTES);
                     const uint64_t b_lo = umma_smem_desc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < UM_BK / 8; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 8 tf32 = 32 bytes along K
-                        ptx::umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-                        ptx::umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                        ptx::umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+                    for (int k = 0; k < UM_BK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 16 fp16 = 32 bytes along K
+                        ptx::umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                        ptx::umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                        ptx::umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
                     }
                     ptx::umma_commit(&empty_bar[stage]);          // smem stage free once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 ptx::umma_commit(&tfull_bar[as]);                 // accumulator complete
+                if (it == 0) TIP_TS(2);
             }
         }
     } else {
-        // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
+        // ================= epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp-2)/4 ====
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int CH = BN / 64;                               // 32-column chunks per warp
+        float* stg = staging + (warp - 2) * 1024;
         const float inv_keep = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
+        const int crow = lane >> 3, cchunk = lane & 7;            // "coal" pattern coordinates
+        const bool vec_ok = (ep.ldc & 3) == 0;
+        const float asc = ep.acc_scale ? __ldg(ep.acc_scale) : 1.f;    // 1 / (s_a * s_w), a power of two
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int m0 = (tile / n_tiles) * UM_BM, n0 = (tile % n_tiles) * BN;
-            const int row = m0 + quarter * 32 + lane;
-            const bool row_ok = row < M;
+            const int rbase = m0 + quarter * 32;                  // first row of this warp
             ptx::mbar_wait(&tfull_bar[as], aphase);
+            if (warp == 2 && it == 0) TIP_TS(3);
             ptx::tc_fence_after();
-            const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+            const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
             float v[32];
-            if constexpr (LN) {
-                // pass 1: x = acc + bias (dropout) + residual, kept in TMEM; row sum
-                float s = 0.f;
+            if constexpr (!LN) {
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = 0; c < CH; ++c) {
+                    const int colb = n0 + half * (BN / 2) + c * 32;     // first column of the chunk
+                    if (colb >= N) break;                                 // warp-uniform
                     ptx::tmem_ld32(t_acc + c * 32, v);
-                    const float* rp = ep.resid + (size_t)row * ep.ldr + c * 32;
-                    const float* rl = ep.resid_lo ? ep.resid_lo + (size_t)row * ep.ldr + c * 32 : nullptr;
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row_ok) {
-                            r = __ldg(reinterpret_cast<const float4*>(rp) + j4);
-                            if (rl) {
-                                const float4 l = __ldg(reinterpret_cast<const float4*>(rl) + j4);
-                                r.x += l.x; r.y += l.y; r.z += l.z; r.w += l.w;
-                            }
-                        }
-                        const float rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int j = j4 * 4 + q, col = c * 32 + j;
-                            float x = v[j] + __ldg(ep.bias + col);
-                            if (ep.drop_p > 0.f) x *= dropout_factor(ep.drop_p, inv_keep, ep.seed, (uint64_t)row * N + col);
-                            x += rr[q];
-                            v[j] = x;
-                            s += x;
+                    stg_write_row(stg, lane, v);
+                    __syncwarp();
+                    const int col = colb + cchunk * 4;
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!(ep.dbg & 2)) {
+                        if (col + 3 < N) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+                        else {
+                            if (col < N) b4.x = __ldg(ep.bias + col);
+                            if (col + 1 < N) b4.y = __ldg(ep.bias + col + 1);
+                            if (col + 2 < N) b4.z = __ldg(ep.bias + col + 2);
                         }
                     }
-                    ptx::tmem_st32(t_acc + c * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + crow, row = rbase + r;
+                        float4 x = *stg_ptr(stg, r, cchunk);
+                        x.x = fmaf(x.x, asc, b4.x); x.y = fmaf(x.y, asc, b4.y); x.z = fmaf(x.z, asc, b4.z); x.w = fmaf(x.w, asc, b4.w);
+                        if (ep.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                        if (ep.drop_p > 0.f) {
+                            const uint64_t id = (uint64_t)row * N + col;
+                            x.x *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id);
+                            x.y *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 1);
+                            x.z *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 2);
+                            x.w *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 3);
+                        }
+                        if (row < M && col < N && !(ep.dbg & 1))
+                            store4(ep.out, ep.out_lo, (size_t)row * ep.ldc + col, N - col, vec_ok, x);
+                    }
+                    __syncwarp();
                 }
-                const float mean = s * (1.f / BN);
+            } else {
+                // ---- pass 1: x = acc + bias (dropout) + residual -> back to TMEM; row sums ----
+                float rsum = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < CH; ++c) {
+                    const int col = half * (BN / 2) + c * 32 + cchunk * 4;
+                    ptx::tmem_ld32(t_acc + c * 32, v);
+                    stg_write_row(stg, lane, v);
+                    __syncwarp();
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + crow, row = rbase + r;
+                        float4 x = *stg_ptr(stg, r, cchunk);
+                        x.x = fmaf(x.x, asc, b4.x); x.y = fmaf(x.y, asc, b4.y); x.z = fmaf(x.z, asc, b4.z); x.w = fmaf(x.w, asc, b4.w);
+                        if (ep.drop_p > 0.f) {
+                            const uint64_t id = (uint64_t)row * N + col;
+                            x.x *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id);
+                            x.y *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 1);
+                            x.z *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 2);
+                            x.w *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 3);
+                        }
+                        if (row < M) {
+                            const size_t e = (size_t)row * ep.ldr + col;
+                            if (ep.resid_lo) {     // FP16 hi/lo planes of ACT_SCALE * residual
+                                const float4 rr = half_pair_load4(reinterpret_cast<const __half*>(ep.resid) + e,
+                                                                  reinterpret_cast<const __half*>(ep.resid_lo) + e);
+                                x.x = fmaf(rr.x, 1.f / ACT_SCALE, x.x); x.y = fmaf(rr.y, 1.f / ACT_SCALE, x.y);
+                                x.z = fmaf(rr.z, 1.f / ACT_SCALE, x.z); x.w = fmaf(rr.w, 1.f / ACT_SCALE, x.w);
+                            } else {
+                                const float4 rh = __ldg(reinterpret_cast<const float4*>(ep.resid + e));
+                                x.x += rh.x; x.y += rh.y; x.z += rh.z; x.w += rh.w;
+                            }
+                        }
+                        *stg_ptr(stg, r, cchunk) = x;
+                    }
+                    __syncwarp();
+                    stg_read_row(stg, lane, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) rsum += v[j];
+                    ptx::tmem_st32(t_acc + c * 32, v);
+                    __syncwarp();
+                }
+                if (warp == 2 && it == 0) TIP_TS(4);
+                row_stat[half * 128 + quarter * 32 + lane] = rsum;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float mean = (row_stat[quarter * 32 + lane] + row_stat[128 + quarter * 32 + lane]) * (1.f / BN);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                // ---- pass 2: centred second moment (thread = row, straight from TMEM) ----
                 float q2 = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = 0; c < CH; ++c) {
                     ptx::tmem_ld32(t_acc + c * 32, v);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; q2 = fmaf(d, d, q2); }
                 }
-                const float rstd = rsqrtf(q2 * (1.f / BN) + 1e-5f);
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    ptx::tmem_ld32(t_acc + c * 32, v);
+                if (warp == 2 && it == 0) TIP_TS(5);
+                row_stat[half * 128 + quarter * 32 + lane] = q2;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float var = (row_stat[quarter * 32 + lane] + row_stat[128 + quarter * 32 + lane]) * (1.f / BN);
+                const float rstd = rsqrtf(var + 1e-5f);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                // mean / rstd of the rows this lane touches in the "coal" pattern
+                float cmean[8], crstd[8];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = c * 32 + j;
-                        v[j] = (v[j] - mean) * rstd * __ldg(ep.gamma + col) + __ldg(ep.beta + col);
-                    }
-                    if (row_ok) {
-                        float* o = ep.out + (size_t)row * ep.ldc + c * 32;
-                        float* ol = ep.out_lo ? ep.out_lo + (size_t)row * ep.ldc + c * 32 : nullptr;
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            if (ol) {
-                                float4 hi, lo;
-                                tf32_split(v[j4 * 4 + 0], hi.x, lo.x); tf32_split(v[j4 * 4 + 1], hi.y, lo.y);
-                                tf32_split(v[j4 * 4 + 2], hi.z, lo.z); tf32_split(v[j4 * 4 + 3], hi.w, lo.w);
-                                reinterpret_cast<float4*>(o)[j4] = hi;
-                                reinterpret_cast<float4*>(ol)[j4] = lo;
-                            } else {
-                                reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                            }
-                        }
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    cmean[i] = __shfl_sync(0xffffffffu, mean, i * 4 + crow);
+                    crstd[i] = __shfl_sync(0xffffffffu, rstd, i * 4 + crow);
                 }
-            } else {
-                const bool vec_ok = (ep.ldc & 3) == 0;
+                // ---- pass 3: normalise, affine, (split,) coalesced store ----
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    const int colb = n0 + c * 32;
-                    if (colb >= N) break;                         // warp-uniform
+                for (int c = 0; c < CH; ++c) {
+                    const int col = half * (BN / 2) + c * 32 + cchunk * 4;
                     ptx::tmem_ld32(t_acc + c * 32, v);
+                    stg_write_row(stg, lane, v);
+                    __syncwarp();
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + col));
+                    const float4 e4 = __ldg(reinterpret_cast<const float4*>(ep.beta + col));
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = colb + j;
-                        float x = v[j] + ((col < N) ? __ldg(ep.bias + col) : 0.f);
-                        if (ep.relu) x = fmaxf(x, 0.f);
-                        if (ep.drop_p > 0.f) x *= dropout_factor(ep.drop_p, inv_keep, ep.seed, (uint64_t)row * N + col);
-                        v[j] = x;
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + crow, row = rbase + r;
+                        float4 x = *stg_ptr(stg, r, cchunk);
+                        x.x = (x.x - cmean[i]) * crstd[i] * g4.x + e4.x;
+                        x.y = (x.y - cmean[i]) * crstd[i] * g4.y + e4.y;
+                        x.z = (x.z - cmean[i]) * crstd[i] * g4.z + e4.z;
+                        x.w = (x.w - cmean[i]) * crstd[i] * g4.w + e4.w;
+                        if (row < M && !(ep.dbg & 1)) store4(ep.out, ep.out_lo, (size_t)row * ep.ldc + col, 4, true, x);
                     }
-                    if (row_ok) {
-                        float* o = ep.out + (size_t)row * ep.ldc + colb;
-                        float* ol = ep.out_lo ? ep.out_lo + (size_t)row * ep.ldc + colb : nullptr;
-                        if (vec_ok && colb + 32 <= N) {
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                if (ol) {
-                                    float4 hi, lo;
-                                    tf32_split(v[j4 * 4 + 0], hi.x, lo.x); tf32_split(v[j4 * 4 + 1], hi.y, lo.y);
-                                    tf32_split(v[j4 * 4 + 2], hi.z, lo.z); tf32_split(v[j4 * 4 + 3], hi.w, lo.w);
-                                    reinterpret_cast<float4*>(o)[j4] = hi;
-                                    reinterpret_cast<float4*>(ol)[j4] = lo;
-                                } else {
-                                    reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if (colb + j < N) {
-                                    if (ol) { float hi, lo; tf32_split(v[j], hi, lo); o[j] = hi; ol[j] = lo; }
-                                    else o[j] = v[j];
-                                }
-                            }
-                        }
-                    }
+                    __syncwarp();
                 }
             }
+            if (warp == 2 && it == 0) TIP_TS(6);
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);     // 4 arrivals free the accumulator
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);     // 8 arrivals free the accumulator
         }
     }
     ptx::tc_fence_before();
@@ -366,6 +449,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
+    if (warp == 2) TIP_TS(7);
+#undef TIP_TS
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -395,15 +480,15 @@ inline tip_encode_tiled_fn umma_encode_fn() {
     return fn;
 }
 
-// 2-D fp32 row-major [rows][cols] plane, box = 32 columns (128 bytes, swizzled) x box_rows rows
-inline bool umma_make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D fp16 row-major [rows][cols] plane, box = 64 columns (128 bytes, swizzled) x box_rows rows
+inline bool umma_make_map(CUtensorMap* map, const __half* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     tip_encode_tiled_fn enc = umma_encode_fn();
     if (!enc) return false;
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstride[1] = {cols * sizeof(float)};
+    cuuint64_t gstride[1] = {cols * sizeof(__half)};
     cuuint32_t box[2] = {(cuuint32_t)UM_BK, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), gdim, gstride, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -412,11 +497,14 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
                            size_t plane_xin, float* xa, float* xb, float* att, size_t plane_e, float* hid,
                            size_t plane_f, float* hs, size_t plane_r, int cap_rows, std::string& err) {
     bool ok = true;
+    // activation planes: hi at the start of the buffer, lo `plane` halves later (same bytes as one fp32 plane)
     auto act = [&](UmmaOperand& op, const float* p, size_t plane, int cols) {
-        ok = ok && umma_make_map(&op.hi, p, cap_rows, cols, UM_BM) && umma_make_map(&op.lo, p + plane, cap_rows, cols, UM_BM);
+        const __half* h = reinterpret_cast<const __half*>(p);
+        ok = ok && umma_make_map(&op.hi, h, cap_rows, cols, UM_BM) && umma_make_map(&op.lo, h + plane, cap_rows, cols, UM_BM);
     };
     auto wgt = [&](UmmaOperand& op, size_t hi, size_t lo, int rows, int cols, int bn) {
-        ok = ok && umma_make_map(&op.hi, blob + hi, rows, cols, bn) && umma_make_map(&op.lo, blob + lo, rows, cols, bn);
+        ok = ok && umma_make_map(&op.hi, reinterpret_cast<const __half*>(blob + hi), rows, cols, bn) &&
+             umma_make_map(&op.lo, reinterpret_cast<const __half*>(blob + lo), rows, cols, bn);
     };
     act(mp.a_xin, xin, plane_xin, d.kin_pad);
     act(mp.a_xa, xa, plane_e, E);
