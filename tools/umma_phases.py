@@ -17,7 +17,7 @@ lib.tip_debug_timestamps.argtypes = [C.c_void_p, C.c_int]
 buf = (C.c_ulonglong * (64 * 8))()
 assert lib.tip_debug_timestamps(buf, 64 * 8) == 0
 names = ["in", "qkv", "out_ln", "ff1", "ff2_ln", "ih", "head_r", "head_e"]
-lab = ["start", "first_full", "mma_issued", "tfull_seen", "ln_pass1", "ln_pass2", "epi_done", "exit"]
+lab = ["start", "first_full|chunk0_done", "mma_issued", "tfull_seen", "ln_pass1|ldtm_done", "ln_pass2|sts_done", "epi_done", "exit"]
 for w in range(8):
     for layer in (0, 16):
         t = [buf[8 * (w + layer) + i] for i in range(8)]

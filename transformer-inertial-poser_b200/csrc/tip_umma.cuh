@@ -169,33 +169,31 @@ __device__ __forceinline__ void stg_read_row(const float* stg, int lane, float (
         v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
 }
-// fp32 output, or (ol != null) FP16 hi/lo planes of ACT_SCALE * x
-__device__ __forceinline__ void store4(float* o, float* ol, size_t off, int ncols_left, bool vec_ok, float4 x) {
-    if (ol) {
-        __half* oh = reinterpret_cast<__half*>(o) + off;
-        __half* olh = reinterpret_cast<__half*>(ol) + off;
-        if (vec_ok && ncols_left >= 4) {
-            half_split_store4(oh, olh, make_float4(x.x * ACT_SCALE, x.y * ACT_SCALE, x.z * ACT_SCALE, x.w * ACT_SCALE));
-        } else {
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (q < ncols_left) { __half hi, lo; half_split(xs[q] * ACT_SCALE, hi, lo); oh[q] = hi; olh[q] = lo; }
-        }
-    } else if (vec_ok && ncols_left >= 4) {
-        *reinterpret_cast<float4*>(o + off) = x;
-    } else {
-        const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (q < ncols_left) o[off + q] = xs[q];
-    }
+// Lean FP16 hi/lo split of four (already scaled) values: Veltkamp splitting in fp32 (hi = x rounded to
+// 11 significant bits, exact in fp16's normal range; lo = x - hi, exact) + two packed conversions
+// per plane, instead of three scalar F2F conversions per value.  Saturates at +-65504.
+__device__ __forceinline__ void veltkamp11(float x, float& hi, float& lo) {
+    x = fminf(fmaxf(x, -65504.f), 65504.f);
+    const float t = __fmul_rn(x, 8193.f);
+    hi = __fsub_rn(t, __fsub_rn(t, x));
+    lo = __fsub_rn(x, hi);
+}
+__device__ __forceinline__ void half_split_store4_fast(__half* hi_p, __half* lo_p, float4 x) {
+    float h0, h1, h2, h3, l0, l1, l2, l3;
+    veltkamp11(x.x, h0, l0); veltkamp11(x.y, h1, l1); veltkamp11(x.z, h2, l2); veltkamp11(x.w, h3, l3);
+    const __half2 ha = __floats2half2_rn(h0, h1), hb = __floats2half2_rn(h2, h3);
+    const __half2 la = __floats2half2_rn(l0, l1), lb = __floats2half2_rn(l2, l3);
+    uint2 uh, ul;
+    uh.x = *reinterpret_cast<const uint32_t*>(&ha); uh.y = *reinterpret_cast<const uint32_t*>(&hb);
+    ul.x = *reinterpret_cast<const uint32_t*>(&la); ul.y = *reinterpret_cast<const uint32_t*>(&lb);
+    *reinterpret_cast<uint2*>(hi_p) = uh;
+    *reinterpret_cast<uint2*>(lo_p) = ul;
 }
 
 constexpr int UM_EPI_WARPS = 8;                 // two warps per TMEM lane quarter (column halves)
 constexpr int UM_THREADS = 64 + 32 * UM_EPI_WARPS;
 
-template <int BN, bool LN>
+template <int BN, bool LN, bool OUT_HALF>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                  const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
@@ -295,91 +293,125 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         const int half = (warp - 2) >> 2;
         constexpr int CH = BN / 64;                               // 32-column chunks per warp
         float* stg = staging + (warp - 2) * 1024;
-        const float inv_keep = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
         const int crow = lane >> 3, cchunk = lane & 7;            // "coal" pattern coordinates
         const bool vec_ok = (ep.ldc & 3) == 0;
         const float asc = ep.acc_scale ? __ldg(ep.acc_scale) : 1.f;    // 1 / (s_a * s_w), a power of two
+        const float osc = OUT_HALF ? ACT_SCALE : 1.f;             // output planes hold ACT_SCALE * x
+        const float relu_floor = ep.relu ? 0.f : -INFINITY;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int m0 = (tile / n_tiles) * UM_BM, n0 = (tile % n_tiles) * BN;
             const int rbase = m0 + quarter * 32;                  // first row of this warp
+            // lean path: full tile, vector stores, no dropout (warp-uniform); everything else -> slow path
+            const bool fast = (m0 + UM_BM <= M) && (n0 + BN <= N) && vec_ok && !(ep.drop_p > 0.f) && !ep.dbg;
             ptx::mbar_wait(&tfull_bar[as], aphase);
             if (warp == 2 && it == 0) TIP_TS(3);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
             float v[32];
             if constexpr (!LN) {
+                if (fast) {
 #pragma unroll 1
-                for (int c = 0; c < CH; ++c) {
-                    const int colb = n0 + half * (BN / 2) + c * 32;     // first column of the chunk
-                    if (colb >= N) break;                                 // warp-uniform
-                    ptx::tmem_ld32(t_acc + c * 32, v);
-                    stg_write_row(stg, lane, v);
-                    __syncwarp();
-                    const int col = colb + cchunk * 4;
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (!(ep.dbg & 2)) {
-                        if (col + 3 < N) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-                        else {
-                            if (col < N) b4.x = __ldg(ep.bias + col);
-                            if (col + 1 < N) b4.y = __ldg(ep.bias + col + 1);
-                            if (col + 2 < N) b4.z = __ldg(ep.bias + col + 2);
-                        }
-                    }
+                    for (int c = 0; c < CH; ++c) {
+                        const int col = n0 + half * (BN / 2) + c * 32 + cchunk * 4;
+                        float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+                        b4.x *= osc; b4.y *= osc; b4.z *= osc; b4.w *= osc;
+                        const float sc = asc * osc;
+                        ptx::tmem_ld32(t_acc + c * 32, v);
+                        stg_write_row(stg, lane, v);
+                        __syncwarp();
+                        const size_t obase = (size_t)(rbase + crow) * ep.ldc + col;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = i * 4 + crow, row = rbase + r;
-                        float4 x = *stg_ptr(stg, r, cchunk);
-                        x.x = fmaf(x.x, asc, b4.x); x.y = fmaf(x.y, asc, b4.y); x.z = fmaf(x.z, asc, b4.z); x.w = fmaf(x.w, asc, b4.w);
-                        if (ep.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                        if (ep.drop_p > 0.f) {
-                            const uint64_t id = (uint64_t)row * N + col;
-                            x.x *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id);
-                            x.y *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 1);
-                            x.z *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 2);
-                            x.w *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 3);
+                        for (int i = 0; i < 8; ++i) {
+                            float4 x = *stg_ptr(stg, i * 4 + crow, cchunk);
+                            x.x = fmaxf(fmaf(x.x, sc, b4.x), relu_floor); x.y = fmaxf(fmaf(x.y, sc, b4.y), relu_floor);
+                            x.z = fmaxf(fmaf(x.z, sc, b4.z), relu_floor); x.w = fmaxf(fmaf(x.w, sc, b4.w), relu_floor);
+                            const size_t off = obase + (size_t)(i * 4) * ep.ldc;
+                            if constexpr (OUT_HALF) half_split_store4_fast(reinterpret_cast<__half*>(ep.out) + off,
+                                                                           reinterpret_cast<__half*>(ep.out_lo) + off, x);
+                            else *reinterpret_cast<float4*>(ep.out + off) = x;
                         }
-                        if (row < M && col < N && !(ep.dbg & 1))
-                            store4(ep.out, ep.out_lo, (size_t)row * ep.ldc + col, N - col, vec_ok, x);
+                        __syncwarp();
                     }
-                    __syncwarp();
+                } else {
+                    const float inv_keep = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
+#pragma unroll 1
+                    for (int c = 0; c < CH; ++c) {
+                        const int colb = n0 + half * (BN / 2) + c * 32;     // first column of the chunk
+                        if (colb >= N) break;                                 // warp-uniform
+                        ptx::tmem_ld32(t_acc + c * 32, v);
+                        stg_write_row(stg, lane, v);
+                        __syncwarp();
+                        const int col = colb + cchunk * 4;
+#pragma unroll 1
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = i * 4 + crow, row = rbase + r;
+                            const float4 x4 = *stg_ptr(stg, r, cchunk);
+                            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (row < M && col + q < N && !(ep.dbg & 1)) {
+                                    float x = fmaf(xs[q], asc, (ep.dbg & 2) ? 0.f : __ldg(ep.bias + col + q));
+                                    x = fmaxf(x, relu_floor);
+                                    if (ep.drop_p > 0.f) x *= dropout_factor(ep.drop_p, inv_keep, ep.seed, (uint64_t)row * N + col + q);
+                                    const size_t off = (size_t)row * ep.ldc + col + q;
+                                    if constexpr (OUT_HALF) {
+                                        __half hi, lo;
+                                        half_split(x * ACT_SCALE, hi, lo);
+                                        reinterpret_cast<__half*>(ep.out)[off] = hi;
+                                        reinterpret_cast<__half*>(ep.out_lo)[off] = lo;
+                                    } else {
+                                        ep.out[off] = x;
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
                 }
             } else {
-                // ---- pass 1: x = acc + bias (dropout) + residual -> back to TMEM; row sums ----
+                // LayerNorm epilogue: out = LN(acc*asc + bias [dropout] + residual) * gamma + beta, BN == 256
+                // == the whole row.  Residual and output are FP16 hi/lo planes of ACT_SCALE * x.
+                const float inv_keep = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
+                const __half* res_hi = reinterpret_cast<const __half*>(ep.resid);
+                const __half* res_lo = reinterpret_cast<const __half*>(ep.resid_lo);
+                // ---- pass 1: x -> back to TMEM; row sums ----
                 float rsum = 0.f;
 #pragma unroll 1
                 for (int c = 0; c < CH; ++c) {
                     const int col = half * (BN / 2) + c * 32 + cchunk * 4;
+                    // residual of this lane's 8 rows first: its latency overlaps the TMEM load + staging
+                    uint2 rh[8], rl[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const size_t e = (size_t)min(rbase + i * 4 + crow, M - 1) * ep.ldr + col;
+                        rh[i] = __ldg(reinterpret_cast<const uint2*>(res_hi + e));
+                        rl[i] = __ldg(reinterpret_cast<const uint2*>(res_lo + e));
+                    }
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
                     ptx::tmem_ld32(t_acc + c * 32, v);
                     stg_write_row(stg, lane, v);
                     __syncwarp();
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int r = i * 4 + crow, row = rbase + r;
+                        const int r = i * 4 + crow;
                         float4 x = *stg_ptr(stg, r, cchunk);
                         x.x = fmaf(x.x, asc, b4.x); x.y = fmaf(x.y, asc, b4.y); x.z = fmaf(x.z, asc, b4.z); x.w = fmaf(x.w, asc, b4.w);
-                        if (ep.drop_p > 0.f) {
-                            const uint64_t id = (uint64_t)row * N + col;
+                        if (!fast && ep.drop_p > 0.f) {
+                            const uint64_t id = (uint64_t)(rbase + r) * N + col;
                             x.x *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id);
                             x.y *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 1);
                             x.z *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 2);
                             x.w *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 3);
                         }
-                        if (row < M) {
-                            const size_t e = (size_t)row * ep.ldr + col;
-                            if (ep.resid_lo) {     // FP16 hi/lo planes of ACT_SCALE * residual
-                                const float4 rr = half_pair_load4(reinterpret_cast<const __half*>(ep.resid) + e,
-                                                                  reinterpret_cast<const __half*>(ep.resid_lo) + e);
-                                x.x = fmaf(rr.x, 1.f / ACT_SCALE, x.x); x.y = fmaf(rr.y, 1.f / ACT_SCALE, x.y);
-                                x.z = fmaf(rr.z, 1.f / ACT_SCALE, x.z); x.w = fmaf(rr.w, 1.f / ACT_SCALE, x.w);
-                            } else {
-                                const float4 rh = __ldg(reinterpret_cast<const float4*>(ep.resid + e));
-                                x.x += rh.x; x.y += rh.y; x.z += rh.z; x.w += rh.w;
-                            }
-                        }
+                        const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&rh[i].x));
+                        const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&rh[i].y));
+                        const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&rl[i].x));
+                        const float2 l1 = __half22float2(*reinterpret_cast<const __half2*>(&rl[i].y));
+                        x.x = fmaf(h0.x + l0.x, 1.f / ACT_SCALE, x.x); x.y = fmaf(h0.y + l0.y, 1.f / ACT_SCALE, x.y);
+                        x.z = fmaf(h1.x + l1.x, 1.f / ACT_SCALE, x.z); x.w = fmaf(h1.y + l1.y, 1.f / ACT_SCALE, x.w);
                         *stg_ptr(stg, r, cchunk) = x;
                     }
                     __syncwarp();
@@ -408,31 +440,40 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                 const float var = (row_stat[quarter * 32 + lane] + row_stat[128 + quarter * 32 + lane]) * (1.f / BN);
                 const float rstd = rsqrtf(var + 1e-5f);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                // mean / rstd of the rows this lane touches in the "coal" pattern
-                float cmean[8], crstd[8];
+                // scale / shift of the rows this lane touches in the "coal" pattern: y = x*a + b with
+                // a = rstd, b = -mean*rstd (then the per-column affine), all pre-multiplied by ACT_SCALE
+                float ca[8], cb[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    cmean[i] = __shfl_sync(0xffffffffu, mean, i * 4 + crow);
-                    crstd[i] = __shfl_sync(0xffffffffu, rstd, i * 4 + crow);
+                    const float mu = __shfl_sync(0xffffffffu, mean, i * 4 + crow);
+                    const float rs = __shfl_sync(0xffffffffu, rstd, i * 4 + crow);
+                    ca[i] = rs;
+                    cb[i] = -mu * rs;
                 }
-                // ---- pass 3: normalise, affine, (split,) coalesced store ----
+                // ---- pass 3: normalise, affine, split, coalesced store ----
 #pragma unroll 1
                 for (int c = 0; c < CH; ++c) {
                     const int col = half * (BN / 2) + c * 32 + cchunk * 4;
+                    float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + col));
+                    float4 e4 = __ldg(reinterpret_cast<const float4*>(ep.beta + col));
+                    g4.x *= ACT_SCALE; g4.y *= ACT_SCALE; g4.z *= ACT_SCALE; g4.w *= ACT_SCALE;
+                    e4.x *= ACT_SCALE; e4.y *= ACT_SCALE; e4.z *= ACT_SCALE; e4.w *= ACT_SCALE;
                     ptx::tmem_ld32(t_acc + c * 32, v);
                     stg_write_row(stg, lane, v);
                     __syncwarp();
-                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + col));
-                    const float4 e4 = __ldg(reinterpret_cast<const float4*>(ep.beta + col));
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int r = i * 4 + crow, row = rbase + r;
                         float4 x = *stg_ptr(stg, r, cchunk);
-                        x.x = (x.x - cmean[i]) * crstd[i] * g4.x + e4.x;
-                        x.y = (x.y - cmean[i]) * crstd[i] * g4.y + e4.y;
-                        x.z = (x.z - cmean[i]) * crstd[i] * g4.z + e4.z;
-                        x.w = (x.w - cmean[i]) * crstd[i] * g4.w + e4.w;
-                        if (row < M && !(ep.dbg & 1)) store4(ep.out, ep.out_lo, (size_t)row * ep.ldc + col, 4, true, x);
+                        x.x = fmaf(fmaf(x.x, ca[i], cb[i]), g4.x, e4.x);
+                        x.y = fmaf(fmaf(x.y, ca[i], cb[i]), g4.y, e4.y);
+                        x.z = fmaf(fmaf(x.z, ca[i], cb[i]), g4.z, e4.z);
+                        x.w = fmaf(fmaf(x.w, ca[i], cb[i]), g4.w, e4.w);
+                        if (row < M) {
+                            const size_t off = (size_t)row * ep.ldc + col;
+                            half_split_store4_fast(reinterpret_cast<__half*>(ep.out) + off,
+                                                   reinterpret_cast<__half*>(ep.out_lo) + off, x);
+                        }
                     }
                     __syncwarp();
                 }
@@ -527,8 +568,9 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&mp.num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (!mp.attrs_set) {
-        cudaFuncSetAttribute(umma_gemm_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES);
-        cudaFuncSetAttribute(umma_gemm_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
         mp.attrs_set = true;
     }
     return TIP_OK;
@@ -550,12 +592,16 @@ inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, c
     const int m_tiles = (M + UM_BM - 1) / UM_BM;
     if (ln) {
         const int tiles = m_tiles;                                // BN = 256 = the whole row
-        umma_gemm_kernel<256, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<256>::SMEM_BYTES, st>>>(
+        umma_gemm_kernel<256, true, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<256>::SMEM_BYTES, st>>>(
             A->hi, A->lo, B->hi, B->lo, M, N, K, ep);
     } else {
         const int tiles = m_tiles * ((N + 127) / 128);
-        umma_gemm_kernel<128, false><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<128>::SMEM_BYTES, st>>>(
-            A->hi, A->lo, B->hi, B->lo, M, N, K, ep);
+        if (ep.out_lo)
+            umma_gemm_kernel<128, false, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<128>::SMEM_BYTES, st>>>(
+                A->hi, A->lo, B->hi, B->lo, M, N, K, ep);
+        else
+            umma_gemm_kernel<128, false, false><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<128>::SMEM_BYTES, st>>>(
+                A->hi, A->lo, B->hi, B->lo, M, N, K, ep);
     }
 }
 
