@@ -413,9 +413,13 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
         m->rnn_clusters = n;
     }
     if (m->rnn_clusters > 0 && !m->rnn_stream_fallback) {
-        const int blocks = (B + RC_ROWS - 1) / RC_ROWS;
-        const int nc = std::min(blocks, m->rnn_clusters);
-        rnn_cluster_kernel<<<nc * RC_CTAS, 256, RC_SMEM_BYTES, st>>>(gi, m->blob + m->off.whh, hs, hs_lo, B, L);
+        // windows per cluster pass: spread the batch over all co-resident clusters, in whole groups of 8
+        const int ncl = m->rnn_clusters;
+        int rpp = (B + ncl - 1) / ncl;
+        rpp = std::min(RC_ROWS, std::max(1, rpp));
+        if (rpp > RC_GROUP) rpp = (rpp + RC_GROUP - 1) / RC_GROUP * RC_GROUP;
+        const int nc = std::min((B + rpp - 1) / rpp, ncl);
+        rnn_cluster_kernel<<<nc * RC_CTAS, 256, RC_SMEM_BYTES, st>>>(gi, m->blob + m->off.whh, hs, hs_lo, B, L, rpp);
         m->launches++;
         return;
     }

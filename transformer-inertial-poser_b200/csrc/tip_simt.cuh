@@ -449,12 +449,13 @@ rnn_stream_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t,
 constexpr int RC_CTAS = 8;                       // CTAs per cluster
 constexpr int RC_UNITS = R / RC_CTAS;            // 64 hidden units per CTA
 constexpr int RC_GROUP = 8;                      // windows per group
-constexpr int RC_ROWS = 2 * RC_GROUP;            // windows per cluster pass
+constexpr int RC_MAXG = 3;                       // groups a cluster interleaves
+constexpr int RC_ROWS = RC_MAXG * RC_GROUP;      // max windows per cluster pass
 constexpr int RC_RPITCH = 72;                    // floats per (slice, window): 2 x (32 + 4 pad)
 constexpr int RC_SLICE = RC_ROWS * RC_RPITCH + 8; // floats per CTA-slice (+32 B: bank spread)
 constexpr int RC_BUF = RC_CTAS * RC_SLICE;       // floats per h buffer
 constexpr int RC_GROUP_BYTES = RC_GROUP * RC_RPITCH * (int)sizeof(float);     // 2304 B per push
-constexpr int RC_SMEM_BYTES = 2 * RC_BUF * (int)sizeof(float) + 64;
+constexpr int RC_SMEM_BYTES = 2 * RC_BUF * (int)sizeof(float) + 128;
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -521,15 +522,15 @@ __device__ __forceinline__ void rc_reduce16(const float (&v)[32], int lane, floa
 // cycles) and the FMA pipes are balanced.
 __global__ void __cluster_dims__(RC_CTAS, 1, 1) __launch_bounds__(256, 1)
 rnn_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh,
-                   float* __restrict__ hs, float* __restrict__ hs_lo, int B, int L) {
-    extern __shared__ __align__(128) float hbuf[];          // [2 buffers][8 slices][16 windows][72] (+pad)
+                   float* __restrict__ hs, float* __restrict__ hs_lo, int B, int L, int rows_per_pass) {
+    extern __shared__ __align__(128) float hbuf[];          // [2 buffers][8 slices][24 windows][72] (+pad)
     const int tid = threadIdx.x, lane = tid & 31;
     const int ug = tid >> 4, s = tid & 15;
     const uint32_t rank = cluster_ctarank();
     const int unit0 = (int)rank * RC_UNITS + ug * 4;         // first of this thread's 4 units
     const int n_clusters = gridDim.x / RC_CTAS, cluster_id = blockIdx.x / RC_CTAS;
     const uint32_t hbuf_s = (uint32_t)__cvta_generic_to_shared(hbuf);
-    const uint32_t bar_s = hbuf_s + 2u * RC_BUF * 4u;        // 4 mbarriers: [group][buffer]
+    const uint32_t bar_s = hbuf_s + 2u * RC_BUF * 4u;        // 2*RC_MAXG mbarriers: [group][buffer]
 
     float w[4][32];                                          // W_hh[unit0 + u][32 s + kk]
 #pragma unroll
@@ -542,7 +543,7 @@ rnn_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh,
         }
     }
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) rc_mbar_init(bar_s + 8u * i, 1);
+        for (int i = 0; i < 2 * RC_MAXG; ++i) rc_mbar_init(bar_s + 8u * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster_arrive();
@@ -557,10 +558,12 @@ rnn_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh,
     // where this thread reads h: k-slice s lives in CTA-slice s/2, half s%2
     const int h_read = (s >> 1) * RC_SLICE + (s & 1) * 36;
 
-    for (int rb = cluster_id; rb * RC_ROWS < B; rb += n_clusters) {
-        const int b0 = rb * RC_ROWS;
-        const int nrows = min(RC_ROWS, B - b0);
-        const int ngroups = nrows > RC_GROUP ? 2 : 1;        // uniform over the cluster
+    // windows are dealt to clusters in blocks of `rows_per_pass` (host-chosen so that one pass covers the
+    // batch whenever B <= clusters * RC_ROWS)
+    for (int rb = cluster_id; rb * rows_per_pass < B; rb += n_clusters) {
+        const int b0 = rb * rows_per_pass;
+        const int nrows = min(rows_per_pass, B - b0);
+        const int ngroups = (nrows + RC_GROUP - 1) / RC_GROUP;   // uniform over the cluster
         for (int t = 0; t < L; ++t) {
             const int cur = t & 1, nxt = cur ^ 1;
             for (int g = 0; g < ngroups; ++g) {
