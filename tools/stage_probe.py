@@ -4,8 +4,10 @@ import torch, numpy as np, contextlib, io
 from bench import build_model, load_weights, synth
 sd, _ = load_weights()
 m = build_model(sd, torch.device('cuda:0'))
+import os
+if os.environ.get('ENGINE'): m.set_gemm_engine(int(os.environ['ENGINE']))
 m.set_profile(True)
-for B in (1, 8, 16, 64, 128, 256, 512):
+for B in [int(b) for b in os.environ.get('BS','1,8,16,64,128,256,512').split(',')]:
     xi, xs = synth(1, B)
     xi, xs = torch.from_numpy(xi).cuda(), torch.from_numpy(xs).cuda()
     for _ in range(3): m(xi, xs)
@@ -14,4 +16,6 @@ for B in (1, 8, 16, 64, 128, 256, 512):
     for _ in range(5):
         m(xi, xs); 
         for n, l, ms in m.profile(): acc.setdefault(n, []).append(ms)
-    print(B, {k: round(float(np.mean(v))*1e3,1) for k, v in acc.items()})
+    d={k: round(float(np.mean(v))*1e3,1) for k, v in acc.items()}
+    tot=sum(v*(4 if k in ('qkv','attention','out_proj_ln','ff1','ff2_ln') else 1) for k,v in d.items())
+    print(B, round(tot,1), d)

@@ -388,7 +388,9 @@ static void launch_sgemm(tip_model* m, cudaStream_t st, const float* A, int lda,
 
 static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, float* out, float* out_lo,
                              int B, int L, float drop_p, uint64_t seed) {
-    if (B >= 32) attention_kernel<2, 4><<<dim3(B, NH / 4), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
+    static const int akind = getenv("TIP_ATTN") ? atoi(getenv("TIP_ATTN")) : 0;
+    if (B >= 32 && akind == 1) attention_kernel<4, 4><<<dim3(B, NH / 4), 320, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
+    else if (B >= 32) attention_kernel<2, 4><<<dim3(B, NH / 4), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
     else         attention_kernel<4, 2><<<dim3(B, NH / 2), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
     m->launches++;
 }

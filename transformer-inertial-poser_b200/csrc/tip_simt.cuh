@@ -237,7 +237,7 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
 //   512-byte-per-row coalesced pieces (HPB=8 heads of one window per CTA).
 //   One thread group of KS lanes owns the query-row pair (p, L-1-p), so every group does the same
 //   L+1 keys of causal work; the KS lanes split the keys and merge (max, sum, o) with shuffles.
-//   Two passes over the keys (max, then exp/accumulate) keep everything in registers.
+//   The lane's scores stay in registers between the max and the exp/accumulate sweeps.
 template <int KS, int HPB>
 __global__ void __launch_bounds__(HPB * 20 * KS)
 attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ out_lo,
@@ -251,16 +251,19 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* 
     const int tid = threadIdx.x;
     const float* base = qkv + (size_t)b * L * (3 * E) + h0 * HD;
 
-    // stage Q, K, V of HPB heads: per row 3 pieces of HPB*16 contiguous floats
+    // stage Q, K, V of HPB heads: per row 3 pieces of HPB*16 contiguous floats, global -> shared with
+    // cp.async (no register staging, all of a thread's 16-byte copies in flight at once)
     constexpr int F4_ROW = HPB * HD / 4;
     for (int i = tid; i < L * 3 * F4_ROW; i += NT) {
         const int row = i / (3 * F4_ROW);
         const int rem = i - row * (3 * F4_ROW);
         const int which = rem / F4_ROW, c4 = rem - which * F4_ROW;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * (3 * E) + which * E) + c4);
-        float* dst = which == 0 ? &Qs[row][0][0] : (which == 1 ? &Ks[row][0][0] : &Vs[row][0][0]);
-        reinterpret_cast<float4*>(dst)[c4] = v;
+        const float* src = base + (size_t)row * (3 * E) + which * E + c4 * 4;
+        float* dst = (which == 0 ? &Qs[row][0][0] : (which == 1 ? &Ks[row][0][0] : &Vs[row][0][0])) + c4 * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const int hl = tid / (20 * KS);
@@ -281,58 +284,62 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* 
         qb[i * 4 + 0] = vb.x; qb[i * 4 + 1] = vb.y; qb[i * 4 + 2] = vb.z; qb[i * 4 + 3] = vb.w;
     }
     const int jend = active ? rb : -1;
-    // pass 1: row maxima
+    // scores of this lane's keys (j = jj*KS + ks) stay in registers; masked / unused slots hold -inf
+    constexpr int NJ = (MAXL + KS - 1) / KS;
+    float sa[NJ], sb[NJ];
     float ma = -INFINITY, mb = -INFINITY;
-    for (int j = ks; j <= jend; j += KS) {
-        float da = 0.f, db = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 kv = *reinterpret_cast<const float4*>(&Ks[j][hl][i * 4]);
-            da = fmaf(qa[i * 4 + 0], kv.x, da); db = fmaf(qb[i * 4 + 0], kv.x, db);
-            da = fmaf(qa[i * 4 + 1], kv.y, da); db = fmaf(qb[i * 4 + 1], kv.y, db);
-            da = fmaf(qa[i * 4 + 2], kv.z, da); db = fmaf(qb[i * 4 + 2], kv.z, db);
-            da = fmaf(qa[i * 4 + 3], kv.w, da); db = fmaf(qb[i * 4 + 3], kv.w, db);
+    for (int jj = 0; jj < NJ; ++jj) {
+        const int j = jj * KS + ks;
+        sa[jj] = -INFINITY;
+        sb[jj] = -INFINITY;
+        if (j <= jend) {
+            float da = 0.f, db = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 kv = *reinterpret_cast<const float4*>(&Ks[j][hl][i * 4]);
+                da = fmaf(qa[i * 4 + 0], kv.x, da); db = fmaf(qb[i * 4 + 0], kv.x, db);
+                da = fmaf(qa[i * 4 + 1], kv.y, da); db = fmaf(qb[i * 4 + 1], kv.y, db);
+                da = fmaf(qa[i * 4 + 2], kv.z, da); db = fmaf(qb[i * 4 + 2], kv.z, db);
+                da = fmaf(qa[i * 4 + 3], kv.w, da); db = fmaf(qb[i * 4 + 3], kv.w, db);
+            }
+            sb[jj] = db;
+            mb = fmaxf(mb, db);
+            if (j <= ra) { sa[jj] = da; ma = fmaxf(ma, da); }
         }
-        mb = fmaxf(mb, db);
-        if (j <= ra) ma = fmaxf(ma, da);
     }
 #pragma unroll
     for (int o = KS >> 1; o > 0; o >>= 1) {
         ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
         mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
     }
-    // pass 2: exp, row sums, P v
+    // exp, row sums, P v   (expf(-inf - m) = 0 for the masked slots)
     float oa[HD], ob[HD], la = 0.f, lb = 0.f;
 #pragma unroll
     for (int i = 0; i < HD; ++i) { oa[i] = 0.f; ob[i] = 0.f; }
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    for (int j = ks; j <= jend; j += KS) {
-        float da = 0.f, db = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 kv = *reinterpret_cast<const float4*>(&Ks[j][hl][i * 4]);
-            da = fmaf(qa[i * 4 + 0], kv.x, da); db = fmaf(qb[i * 4 + 0], kv.x, db);
-            da = fmaf(qa[i * 4 + 1], kv.y, da); db = fmaf(qb[i * 4 + 1], kv.y, db);
-            da = fmaf(qa[i * 4 + 2], kv.z, da); db = fmaf(qb[i * 4 + 2], kv.z, db);
-            da = fmaf(qa[i * 4 + 3], kv.w, da); db = fmaf(qb[i * 4 + 3], kv.w, db);
-        }
-        float pa = (j <= ra) ? expf(da - ma) : 0.f;
-        float pb = expf(db - mb);
-        la += pa;
-        lb += pb;
-        if (drop_p > 0.f) {   // attention-probability dropout (train mode only)
-            const uint64_t ida = (((uint64_t)b * NH + h0 + hl) * MAXL + ra) * MAXL + j;
-            const uint64_t idb = (((uint64_t)b * NH + h0 + hl) * MAXL + rb) * MAXL + j;
-            pa *= dropout_factor(drop_p, inv_keep, seed, ida);
-            pb *= dropout_factor(drop_p, inv_keep, seed, idb);
-        }
+    for (int jj = 0; jj < NJ; ++jj) {
+        const int j = jj * KS + ks;
+        if (j <= jend) {
+            float pa = expf(sa[jj] - ma);
+            float pb = expf(sb[jj] - mb);
+            la += pa;
+            lb += pb;
+            if (drop_p > 0.f) {   // attention-probability dropout (train mode only)
+                const uint64_t ida = (((uint64_t)b * NH + h0 + hl) * MAXL + ra) * MAXL + j;
+                const uint64_t idb = (((uint64_t)b * NH + h0 + hl) * MAXL + rb) * MAXL + j;
+                pa *= dropout_factor(drop_p, inv_keep, seed, ida);
+                pb *= dropout_factor(drop_p, inv_keep, seed, idb);
+            }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 vv = *reinterpret_cast<const float4*>(&Vs[j][hl][i * 4]);
-            oa[i * 4 + 0] = fmaf(pa, vv.x, oa[i * 4 + 0]); ob[i * 4 + 0] = fmaf(pb, vv.x, ob[i * 4 + 0]);
-            oa[i * 4 + 1] = fmaf(pa, vv.y, oa[i * 4 + 1]); ob[i * 4 + 1] = fmaf(pb, vv.y, ob[i * 4 + 1]);
-            oa[i * 4 + 2] = fmaf(pa, vv.z, oa[i * 4 + 2]); ob[i * 4 + 2] = fmaf(pb, vv.z, ob[i * 4 + 2]);
-            oa[i * 4 + 3] = fmaf(pa, vv.w, oa[i * 4 + 3]); ob[i * 4 + 3] = fmaf(pb, vv.w, ob[i * 4 + 3]);
+            for (int i = 0; i < 4; ++i) {
+                const float4 vv = *reinterpret_cast<const float4*>(&Vs[j][hl][i * 4]);
+                oa[i * 4 + 0] = fmaf(pa, vv.x, oa[i * 4 + 0]); ob[i * 4 + 0] = fmaf(pb, vv.x, ob[i * 4 + 0]);
+                oa[i * 4 + 1] = fmaf(pa, vv.y, oa[i * 4 + 1]); ob[i * 4 + 1] = fmaf(pb, vv.y, ob[i * 4 + 1]);
+                oa[i * 4 + 2] = fmaf(pa, vv.z, oa[i * 4 + 2]); ob[i * 4 + 2] = fmaf(pb, vv.z, ob[i * 4 + 2]);
+                oa[i * 4 + 3] = fmaf(pa, vv.w, oa[i * 4 + 3]); ob[i * 4 + 3] = fmaf(pb, vv.w, ob[i * 4 + 3]);
+            }
         }
     }
 #pragma unroll
