@@ -130,8 +130,8 @@ int  tip_stream_length(const tip_model* m);   /* current L (0 before the first p
 int  tip_algorithmic_cost(const tip_model* m, int B, int L, double* bytes, double* flops);
 /* Number of kernels the last tip_forward launched (for bench.py's gpu_launches). */
 int  tip_last_launch_count(const tip_model* m);
-/* Select the GEMM engine: 0 = auto (tcgen05 3xTF32 when B*L >= 512, FFMA otherwise),
- * 1 = force FFMA fp32 kernels, 2 = force tcgen05 3xTF32 kernels. */
+/* Select the GEMM engine: 0 = auto (= 2), 1 = FFMA fp32 kernels (cross-check engine),
+ * 2 = tcgen05 3xFP16-split tensor-core kernels. */
 int  tip_set_gemm_engine(tip_model* m, int engine);
 /* CUDA-graph the forward for a fixed (B, L) (used by the streaming path); 0 disables. */
 int  tip_set_use_graphs(tip_model* m, int enable);

@@ -1,6 +1,6 @@
 """Phase timestamps of CTA 0 of the tcgen05 GEMMs (debug build hook TIP_DBG=4)."""
 import ctypes as C, os, sys
-os.environ["TIP_DBG"] = "4"
+os.environ["TIP_TS"] = "1"
 sys.path.insert(0, 'transformer-inertial-poser_b200'); sys.path.insert(0, '.')
 import torch, numpy as np
 from bench import build_model, load_weights, synth

@@ -447,11 +447,11 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
     const float p_past = drop ? drop->past_state_dropout : 0.f;
     const float p_enc = drop ? drop->encoder_dropout : 0.f;
     const uint64_t seed = drop ? drop->seed : 0;
-    const bool umma = (m->engine == 2) || (m->engine == 0 && UMMA_AVAILABLE && M >= 512);
+    const bool umma = (m->engine == 2) || (m->engine == 0 && UMMA_AVAILABLE);
     if (umma) {
         if (!m->maps_ready) {
             rc = umma_build_maps(m->maps, m->blob, o, d, m->xin, m->plane_xin, m->xa, m->xb, m->att,
-                                 m->plane_e, m->hid, m->plane_f, m->hs, m->plane_r, m->cap_rows, m->err);
+                                 m->plane_e, m->hid, m->plane_f, m->hs, m->plane_r, m->qkv, m->gi, m->cap_rows, m->err);
             if (rc != TIP_OK) return rc;
             m->maps_ready = true;
         }
@@ -481,7 +481,8 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
             static const int dbg = getenv("TIP_DBG") ? atoi(getenv("TIP_DBG")) : 0;
             ep.dbg = dbg;
             ep.tbuf = nullptr;
-            if (dbg & 4) {
+            static const int ts_on = getenv("TIP_TS") ? atoi(getenv("TIP_TS")) : 0;
+            if ((dbg & 4) || ts_on) {
                 static unsigned long long* tb = nullptr;
                 if (!tb) cudaMalloc(&tb, 64 * 32 * sizeof(unsigned long long));
                 ep.tbuf = tb + 8 * (which + (layer > 0 ? 16 : 0));
@@ -686,10 +687,10 @@ extern "C" int tip_stream_step(tip_model* m, const float* imu_row, const float* 
         if (!m->st_graph) {
             rc = ensure_workspace(m, (int)S * MAXL);
             if (rc != TIP_OK) return rc;
-            if ((m->engine == 2 || (m->engine == 0 && UMMA_AVAILABLE && (int)S * MAXL >= 512)) && !m->maps_ready) {
+            if ((m->engine == 2 || (m->engine == 0 && UMMA_AVAILABLE)) && !m->maps_ready) {
                 // descriptors must exist before capture (their creation is host work)
                 rc = umma_build_maps(m->maps, m->blob, m->off, m->d, m->xin, m->plane_xin, m->xa, m->xb, m->att,
-                                     m->plane_e, m->hid, m->plane_f, m->hs, m->plane_r, m->cap_rows, m->err);
+                                     m->plane_e, m->hid, m->plane_f, m->hs, m->plane_r, m->qkv, m->gi, m->cap_rows, m->err);
                 if (rc != TIP_OK) return rc;
                 m->maps_ready = true;
             }

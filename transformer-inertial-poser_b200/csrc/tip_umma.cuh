@@ -79,6 +79,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -197,6 +205,7 @@ template <int BN, bool LN, bool OUT_HALF>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                  const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+                 const __grid_constant__ CUtensorMap mapC0, const __grid_constant__ CUtensorMap mapC1,
                  int M, int N, int K, Epi ep) {
     using Cfg = UmmaCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -305,14 +314,72 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
             const int m0 = (tile / n_tiles) * UM_BM, n0 = (tile % n_tiles) * BN;
             const int rbase = m0 + quarter * 32;                  // first row of this warp
             // lean path: full tile, vector stores, no dropout (warp-uniform); everything else -> slow path
-            const bool fast = (m0 + UM_BM <= M) && (n0 + BN <= N) && vec_ok && !(ep.drop_p > 0.f) && !ep.dbg;
+            const bool fast = (m0 + UM_BM <= M) && (n0 + BN <= N) && vec_ok && !(ep.drop_p > 0.f) && !(ep.dbg & 7);
             ptx::mbar_wait(&tfull_bar[as], aphase);
             if (warp == 2 && it == 0) TIP_TS(3);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
             float v[32];
             if constexpr (!LN) {
-                if (fast) {
+                if (ep.tma_out && (n0 + BN <= N) && !(ep.drop_p > 0.f) && !(ep.dbg & 7)) {
+                    // thread = accumulator row: bias/ReLU/split in registers, 32x32 output box through a
+                    // swizzled 4 KB shared tile, written to global by TMA (no transposition, no LSU stores)
+                    const float sc = asc * osc;
+                    uint8_t* sbuf = reinterpret_cast<uint8_t*>(stg);
+#pragma unroll 1
+                    for (int c = 0; c < CH; ++c) {
+                        const int colb = n0 + half * (BN / 2) + c * 32;
+                        ptx::tmem_ld32(t_acc + c * 32, v);
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + colb) + j4);   // warp-uniform
+                            v[4 * j4 + 0] = fmaxf(fmaf(v[4 * j4 + 0], sc, b.x * osc), relu_floor);
+                            v[4 * j4 + 1] = fmaxf(fmaf(v[4 * j4 + 1], sc, b.y * osc), relu_floor);
+                            v[4 * j4 + 2] = fmaxf(fmaf(v[4 * j4 + 2], sc, b.z * osc), relu_floor);
+                            v[4 * j4 + 3] = fmaxf(fmaf(v[4 * j4 + 3], sc, b.w * osc), relu_floor);
+                        }
+                        if (lane == 0) ptx::bulk_wait_read0();        // previous box has left the shared tile
+                        __syncwarp();
+                        if constexpr (OUT_HALF) {
+                            // two [32 rows][64 B] tiles (hi, lo), 64B-swizzled: chunk ^= (row >> 1) & 3
+                            const int sw = (lane >> 1) & 3;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 uh, ul;
+                                float h0, h1, l0, l1;
+                                __half2 t;
+                                veltkamp11(v[8 * j + 0], h0, l0); veltkamp11(v[8 * j + 1], h1, l1);
+                                t = __floats2half2_rn(h0, h1); uh.x = *reinterpret_cast<uint32_t*>(&t);
+                                t = __floats2half2_rn(l0, l1); ul.x = *reinterpret_cast<uint32_t*>(&t);
+                                veltkamp11(v[8 * j + 2], h0, l0); veltkamp11(v[8 * j + 3], h1, l1);
+                                t = __floats2half2_rn(h0, h1); uh.y = *reinterpret_cast<uint32_t*>(&t);
+                                t = __floats2half2_rn(l0, l1); ul.y = *reinterpret_cast<uint32_t*>(&t);
+                                veltkamp11(v[8 * j + 4], h0, l0); veltkamp11(v[8 * j + 5], h1, l1);
+                                t = __floats2half2_rn(h0, h1); uh.z = *reinterpret_cast<uint32_t*>(&t);
+                                t = __floats2half2_rn(l0, l1); ul.z = *reinterpret_cast<uint32_t*>(&t);
+                                veltkamp11(v[8 * j + 6], h0, l0); veltkamp11(v[8 * j + 7], h1, l1);
+                                t = __floats2half2_rn(h0, h1); uh.w = *reinterpret_cast<uint32_t*>(&t);
+                                t = __floats2half2_rn(l0, l1); ul.w = *reinterpret_cast<uint32_t*>(&t);
+                                const int off = lane * 64 + ((j ^ sw) << 4);
+                                *reinterpret_cast<uint4*>(sbuf + off) = uh;
+                                *reinterpret_cast<uint4*>(sbuf + 2048 + off) = ul;
+                            }
+                        } else {
+                            // one [32 rows][128 B] fp32 tile, 128B-swizzled: chunk ^= row & 7
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                *reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
+                        ptx::fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&mapC0, sbuf, colb, rbase);
+                            if constexpr (OUT_HALF) ptx::tma_store_2d(&mapC1, sbuf + 2048, colb, rbase);
+                            ptx::bulk_commit();
+                        }
+                    }
+                } else if (fast) {
 #pragma unroll 1
                     for (int c = 0; c < CH; ++c) {
                         const int col = n0 + half * (BN / 2) + c * 32 + cchunk * 4;
@@ -329,6 +396,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                             x.x = fmaxf(fmaf(x.x, sc, b4.x), relu_floor); x.y = fmaxf(fmaf(x.y, sc, b4.y), relu_floor);
                             x.z = fmaxf(fmaf(x.z, sc, b4.z), relu_floor); x.w = fmaxf(fmaf(x.w, sc, b4.w), relu_floor);
                             const size_t off = obase + (size_t)(i * 4) * ep.ldc;
+                            if (ep.dbg & 8) { if (x.x == 123.456f) ep.out[off] = x.y; continue; }     // experiment: no stores
+                            if (ep.dbg & 16) {                                                         // experiment: no split math
+                                if constexpr (OUT_HALF) { *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out) + off) = make_uint2(__float_as_uint(x.x), __float_as_uint(x.y));
+                                    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_lo) + off) = make_uint2(__float_as_uint(x.z), __float_as_uint(x.w)); continue; }
+                            }
                             if constexpr (OUT_HALF) half_split_store4_fast(reinterpret_cast<__half*>(ep.out) + off,
                                                                            reinterpret_cast<__half*>(ep.out_lo) + off, x);
                             else *reinterpret_cast<float4*>(ep.out + off) = x;
@@ -484,6 +556,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);     // 8 arrivals free the accumulator
         }
     }
+    if (warp >= 2 && lane == 0) ptx::bulk_wait0();                 // outstanding TMA stores of this warp
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -497,9 +570,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
 // ------------------------------------------------------------------------------------------------
 // Host side: TMA descriptors of every operand plane and the launch table.
 struct UmmaOperand { CUtensorMap hi, lo; };
+struct UmmaOutput { CUtensorMap c0, c1; bool valid = false; };   // 32x32 store boxes (hi/lo fp16 planes, or one fp32 plane)
 struct UmmaMaps {
     UmmaOperand a_xin, a_xa, a_xb, a_att, a_hid, a_hs;                    // activations (box 32 x 128)
     UmmaOperand w_in, w_qkv[MAX_LAYERS], w_o[MAX_LAYERS], w_1[MAX_LAYERS], w_2[MAX_LAYERS], w_ih, w_l;
+    UmmaOutput o_xa, o_xb, o_hid, o_qkv, o_gi;                             // TMA-store targets
     int num_sms = 148;
     bool attrs_set = false;
 };
@@ -534,10 +609,40 @@ inline bool umma_make_map(CUtensorMap* map, const __half* base, uint64_t rows, u
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// output box: 32 rows x 32 columns; fp16 planes (64-byte rows, SWIZZLE_64B) or fp32 (128-byte rows, SWIZZLE_128B)
+inline bool umma_make_store_map(CUtensorMap* map, void* base, bool is_half, uint64_t rows, uint64_t cols) {
+    tip_encode_tiled_fn enc = umma_encode_fn();
+    if (!enc) return false;
+    const size_t es = is_half ? sizeof(__half) : sizeof(float);
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * es};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, is_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride,
+               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, is_half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, const Dims& d, float* xin,
                            size_t plane_xin, float* xa, float* xb, float* att, size_t plane_e, float* hid,
-                           size_t plane_f, float* hs, size_t plane_r, int cap_rows, std::string& err) {
+                           size_t plane_f, float* hs, size_t plane_r, float* qkv, float* gi, int cap_rows,
+                           std::string& err) {
     bool ok = true;
+    auto outp = [&](UmmaOutput& op, float* p, size_t plane, int cols, bool is_half) {
+        if (is_half) {
+            __half* h = reinterpret_cast<__half*>(p);
+            op.valid = umma_make_store_map(&op.c0, h, true, cap_rows, cols) && umma_make_store_map(&op.c1, h + plane, true, cap_rows, cols);
+        } else {
+            op.valid = umma_make_store_map(&op.c0, p, false, cap_rows, cols);
+            op.c1 = op.c0;
+        }
+        ok = ok && op.valid;
+    };
+    outp(mp.o_xa, xa, plane_e, E, true);
+    outp(mp.o_xb, xb, plane_e, E, true);
+    outp(mp.o_hid, hid, plane_f, F, true);
+    outp(mp.o_qkv, qkv, 0, 3 * E, false);
+    outp(mp.o_gi, gi, 0, R, false);
     // activation planes: hi at the start of the buffer, lo `plane` halves later (same bytes as one fp32 plane)
     auto act = [&](UmmaOperand& op, const float* p, size_t plane, int cols) {
         const __half* h = reinterpret_cast<const __half*>(p);
@@ -576,32 +681,37 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
     return TIP_OK;
 }
 
-inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, const Epi& ep, bool ln,
+inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, const Epi& ep_in, bool ln,
                       cudaStream_t st) {
     const UmmaOperand *A = nullptr, *B = nullptr;
+    const UmmaOutput* C = nullptr;
     switch (which) {
-        case UG_IN:     A = &mp.a_xin; B = &mp.w_in; break;
-        case UG_QKV:    A = &mp.a_xa;  B = &mp.w_qkv[layer]; break;
-        case UG_OUT:    A = &mp.a_att; B = &mp.w_o[layer]; break;
-        case UG_FF1:    A = &mp.a_xb;  B = &mp.w_1[layer]; break;
-        case UG_FF2:    A = &mp.a_hid; B = &mp.w_2[layer]; break;
-        case UG_IH:     A = &mp.a_xa;  B = &mp.w_ih; break;
-        case UG_HEAD_R: A = &mp.a_hs;  B = &mp.w_l; break;
+        case UG_IN:     A = &mp.a_xin; B = &mp.w_in; C = &mp.o_xa; break;
+        case UG_QKV:    A = &mp.a_xa;  B = &mp.w_qkv[layer]; C = &mp.o_qkv; break;
+        case UG_OUT:    A = &mp.a_att; B = &mp.w_o[layer]; C = &mp.o_xb; break;
+        case UG_FF1:    A = &mp.a_xb;  B = &mp.w_1[layer]; C = &mp.o_hid; break;
+        case UG_FF2:    A = &mp.a_hid; B = &mp.w_2[layer]; C = &mp.o_xa; break;
+        case UG_IH:     A = &mp.a_xa;  B = &mp.w_ih; C = &mp.o_gi; break;
+        case UG_HEAD_R: A = &mp.a_hs;  B = &mp.w_l; break;      // y (ldc = size_s, unaligned): plain stores
         default:        A = &mp.a_xa;  B = &mp.w_l; break;      // UG_HEAD_E
     }
+    Epi ep = ep_in;
+    ep.tma_out = (C && C->valid && !getenv("TIP_NO_TMA_STORE")) ? 1 : 0;
+    const CUtensorMap& c0 = C ? C->c0 : A->hi;
+    const CUtensorMap& c1 = C ? C->c1 : A->lo;
     const int m_tiles = (M + UM_BM - 1) / UM_BM;
     if (ln) {
         const int tiles = m_tiles;                                // BN = 256 = the whole row
         umma_gemm_kernel<256, true, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<256>::SMEM_BYTES, st>>>(
-            A->hi, A->lo, B->hi, B->lo, M, N, K, ep);
+            A->hi, A->lo, B->hi, B->lo, c0, c1, M, N, K, ep);
     } else {
         const int tiles = m_tiles * ((N + 127) / 128);
         if (ep.out_lo)
             umma_gemm_kernel<128, false, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<128>::SMEM_BYTES, st>>>(
-                A->hi, A->lo, B->hi, B->lo, M, N, K, ep);
+                A->hi, A->lo, B->hi, B->lo, c0, c1, M, N, K, ep);
         else
             umma_gemm_kernel<128, false, false><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<128>::SMEM_BYTES, st>>>(
-                A->hi, A->lo, B->hi, B->lo, M, N, K, ep);
+                A->hi, A->lo, B->hi, B->lo, c0, c1, M, N, K, ep);
     }
 }
 
