@@ -284,6 +284,30 @@ def main():
     h2d = B * L_WIN * (90 + 131) * 4
     d2h = B * L_WIN * 131 * 4
 
+    # ---- BASELINE configs[2]: one stream, frame-by-frame (B=1, L ramps 1..40 then slides), host rows in,
+    #      last output row back, closed loop; p50 / p99 per-frame latency of the public streaming call
+    stream_lat = None
+    if rank == 0 and world == 1:
+        from tip_b200.streaming import StreamSession
+        sess = StreamSession(model, n_streams=1)
+        xi, xs = synth(2, 1)
+        rs = np.random.RandomState(2)
+        imu_rows = rs.standard_normal((700, 90)).astype(np.float32)
+        s_row = xs[0, 0].copy()
+        s_row[np.isnan(s_row)] = 0
+        lat = []
+        for t in range(700):
+            t0 = time.perf_counter()
+            y = sess.step(imu_rows[t][None], s_row[None])
+            lat.append(time.perf_counter() - t0)
+            s_row = np.clip(y[0], -10, 10)               # feed the prediction back (load generator only)
+        lat = np.array(lat[100:]) * 1e6                   # steady state (L = 40, CUDA-graphed frame)
+        stream_lat = {"frames": int(lat.size), "p50_us": float(np.percentile(lat, 50)),
+                      "p99_us": float(np.percentile(lat, 99)), "mean_us": float(lat.mean()),
+                      "fps_single_stream": float(1e6 / lat.mean()),
+                      "what": "StreamSession.step with host rows: H2D of one (90,)+(131,) row, window shift, "
+                              "forward B=1 L=40, D2H of the last row, stream sync"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -346,6 +370,8 @@ def main():
         "roofline": roofline,
         "wall_s_timed_region": t_wall,
     }
+    if stream_lat:
+        out["stream_latency"] = stream_lat
     if cpu_baseline:
         out["cpu_baseline"] = cpu_baseline
     print(json.dumps(out))

@@ -8,11 +8,13 @@
 #include "tip_common.cuh"
 #include "tip_simt.cuh"
 #include "tip_umma.cuh"
+#include "tip_rnn_umma.cuh"
 
 using namespace tip;
 
 namespace {
 unsigned long long* g_tbuf = nullptr;
+unsigned long long* g_rnn_tbuf = nullptr;
 std::string g_create_error;
 constexpr int CHUNK_WINDOWS = 1024;   // windows per pass through the workspace
 }  // namespace
@@ -29,6 +31,7 @@ struct tip_model {
     int launches = 0;
     int64_t last_rows = 0;
     int rnn_clusters = -1;          // co-schedulable 8-CTA clusters (queried on first use)
+    int rnn_umma_clusters = -1;
     int rnn_stream_fallback = 0;    // TIP_RNN_STREAM=1: L2-streaming kernel (debug / comparison)
     std::string err;
 
@@ -101,6 +104,7 @@ static void compute_offsets(tip_model* m) {
         o.wih = take((size_t)R * E); o.brnn = take(R);
         o.whh = take((size_t)R * R); o.whh_t = take((size_t)R * R);
         o.wih_hi = take((size_t)R * E); o.wih_lo = take((size_t)R * E);
+        o.whh_hi = take((size_t)R * R); o.whh_lo = take((size_t)R * R);
     }
     o.wl = take((size_t)HEAD_NPAD * d.khead); o.bl = take(HEAD_NPAD);
     o.wl_hi = take((size_t)HEAD_NPAD * d.khead); o.wl_lo = take((size_t)HEAD_NPAD * d.khead);
@@ -249,6 +253,7 @@ extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64
         pack_transpose_kernel<<<dim3(R / 32, R / 32), dim3(32, 32), 0, st>>>(t[i + 1], B + o.whh_t, R);
         pack_add_kernel<<<(R + 255) / 256, 256, 0, st>>>(t[i + 2], t[i + 3], B + o.brnn, R);
         split(o.wih, o.wih_hi, o.wih_lo, (size_t)R * E, SC_IH, ACT_SCALE);
+        split(o.whh, o.whh_hi, o.whh_lo, (size_t)R * R, SC_HH, ACT_SCALE);
         i += 4;
     }
     pack_pad_rows_kernel<<<(HEAD_NPAD * d.khead + 255) / 256, 256, 0, st>>>(t[i], B + o.wl, d.size_s, HEAD_NPAD, d.khead);
@@ -287,6 +292,10 @@ extern "C" int tip_set_use_graphs(tip_model* m, int enable) {
 }
 extern "C" int tip_last_launch_count(const tip_model* m) { return m ? m->launches : 0; }
 
+extern "C" int tip_debug_rnn_timestamps(unsigned long long* host_out) {
+    if (!g_rnn_tbuf) { cudaMalloc(&g_rnn_tbuf, 64); cudaMemset(g_rnn_tbuf, 0, 64); return TIP_OK; }
+    return cudaMemcpy(host_out, g_rnn_tbuf, 64, cudaMemcpyDeviceToHost) == cudaSuccess ? TIP_OK : TIP_ERR_CUDA;
+}
 extern "C" int tip_debug_timestamps(unsigned long long* host_out, int n) {
     if (!g_tbuf || n > 64 * 32) return TIP_ERR_INVALID_ARG;
     return cudaMemcpy(host_out, g_tbuf, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? TIP_OK : TIP_ERR_CUDA;
@@ -413,6 +422,28 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
         if (getenv("TIP_RNN_CLUSTERS")) n = atoi(getenv("TIP_RNN_CLUSTERS"));
         if (getenv("TIP_VERBOSE")) fprintf(stderr, "[tip] rnn clusters co-schedulable: %d\n", n);
         m->rnn_clusters = n;
+    }
+    static const int rnn_kind = getenv("TIP_RNN") ? atoi(getenv("TIP_RNN")) : 0;   // 1: force the FFMA cluster kernel
+    if (hs_lo && m->maps_ready && rnn_kind != 1 && !m->rnn_stream_fallback) {
+        // tensor-core recurrence (tcgen05 engine): clusters of 8 CTAs, RU_N windows each
+        if (m->rnn_umma_clusters < 0) {
+            cudaFuncSetAttribute(rnn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM_BYTES);
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(RU_CTAS * 18); q.blockDim = dim3(RU_THREADS); q.dynamicSmemBytes = RU_SMEM_BYTES;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, rnn_umma_kernel, &q) != cudaSuccess || n < 1) { n = 0; cudaGetLastError(); }
+            if (getenv("TIP_VERBOSE")) fprintf(stderr, "[tip] rnn_umma clusters co-schedulable: %d\n", n);
+            m->rnn_umma_clusters = n;
+        }
+        if (m->rnn_umma_clusters > 0) {
+            const int blocks = (B + RU_N - 1) / RU_N;
+            const int nc = std::min(blocks, m->rnn_umma_clusters);
+            rnn_umma_kernel<<<nc * RU_CTAS, RU_THREADS, RU_SMEM_BYTES, st>>>(
+                m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
+                m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf);
+            m->launches++;
+            return;
+        }
     }
     if (m->rnn_clusters > 0 && !m->rnn_stream_fallback) {
         // windows per cluster pass: spread the batch over all co-resident clusters, in whole groups of 8

@@ -30,7 +30,7 @@ struct LayerOff {
 };
 // index of a matrix in the `scales` table
 constexpr int SC_IN = 0, SC_LAYER0 = 1 /* + 4*layer + {qkv,o,1,2} */, SC_IH = 1 + 4 * MAX_LAYERS, SC_HEAD = SC_IH + 1,
-              SC_COUNT = SC_HEAD + 1;
+              SC_HH = SC_HEAD + 1, SC_COUNT = SC_HH + 1;
 // activations are stored as FP16 hi/lo planes of ACT_SCALE * x (|x| < 4096 representable; the
 // model's LayerNorm / ReLU / tanh outputs stay below ~20), the raw model input with scale 1.
 constexpr float ACT_SCALE = 16.f;
@@ -38,6 +38,7 @@ struct PackOff {
     size_t win, bin, win_hi, win_lo;          // [E][kin_pad]
     LayerOff layer[MAX_LAYERS];
     size_t wih, brnn, whh, whh_t, wih_hi, wih_lo;   // whh [R][R] (out,in);  whh_t [R k][R n]
+    size_t whh_hi, whh_lo;                          // FP16 planes of s_w * W_hh (tensor-core recurrence)
     size_t wl, bl, wl_hi, wl_lo;              // head [HEAD_NPAD][khead] zero padded rows
     size_t scales;                            // [SC_COUNT] accumulator un-scale factors
     size_t total;

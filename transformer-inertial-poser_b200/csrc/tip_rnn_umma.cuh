@@ -1,0 +1,220 @@
+// tanh RNN recurrence on the tensor cores (reference simple_transformer_with_state.py:95-99):
+//   h_t = tanh(gi[:, t, :] + W_hh h_{t-1}),  h_0 = 0,  gi = x W_ih^T + b_ih + b_hh (previous GEMM).
+//
+// The recurrence is the path's only serial chain.  A thread-block cluster of 8 CTAs carries up to
+// RU_N = 24 windows through all L steps:
+//   * CTA c owns hidden units [64c, 64c+64).  Its slice of W_hh (FP16 hi/lo planes of s_w * W_hh,
+//     128 KB) is TMA-loaded ONCE into 128B-swizzled shared memory and stays resident as the A
+//     operand; nothing is re-streamed from L2 inside the time loop.  The hi and lo rows are STACKED
+//     along M (128 rows per k-block; TMEM quarter q holds [hi rows of units 16q..16q+15 | lo rows
+//     of the same units]) ...
+//   * ... and the B operand stacks the FP16 hi/lo planes of 16*h_{t-1} along N (48 rows per k-block:
+//     24 windows hi, 24 windows lo), so ONE tcgen05.mma.kind::f16 (M=128, N=48, K=16) per k-step
+//     yields all partial products of the error-compensated split (hi*hi, hi*lo, lo*hi, lo*lo): 32
+//     MMAs per time step instead of 96.  The issue rate of the single MMA thread, not the tensor
+//     pipe, bounds this tiny GEMM, so fewer/larger instructions are what matters.
+//   * eight epilogue warps read the accumulator (tcgen05.ld), fold the four partial products (two
+//     column groups + a lane^16 shuffle), add gi, apply tanh, split to FP16 hi/lo and write this
+//     CTA's k-block of the next B operand in the swizzled layout;
+//   * that k-block (6 KB) is pushed to the 7 peer CTAs with cp.async.bulk.shared::cluster, the bytes
+//     counted on an mbarrier in each destination, which is also what the MMA issuer of the next step
+//     waits on -- no cluster-wide barrier in the loop.  B is double-buffered over the step parity.
+#pragma once
+#include "tip_umma.cuh"
+
+namespace tip {
+
+constexpr int RU_CTAS = 8;
+constexpr int RU_UNITS = R / RU_CTAS;                 // 64 hidden units per CTA (128 stacked A rows)
+constexpr int RU_N = 24;                              // windows per cluster pass (48 stacked B rows)
+constexpr int RU_EPI_WARPS = 8;
+constexpr int RU_THREADS = 32 + 32 * RU_EPI_WARPS;    // warp 0: MMA issuer / TMEM owner; warps 1..8: epilogue
+constexpr int RU_A_KB_BYTES = 2 * RU_UNITS * 128;     // 16 KB: one k-block (64 k) of the stacked W_hh slice
+constexpr int RU_A_BYTES = 8 * RU_A_KB_BYTES;         // 128 KB
+constexpr int RU_B_KB_BYTES = 2 * RU_N * 128;         // 6 KB: one k-block of stacked h (hi rows, then lo rows)
+constexpr int RU_B_BYTES = 8 * RU_B_KB_BYTES;         // 48 KB per parity
+constexpr int RU_SMEM_BYTES = RU_A_BYTES + 2 * RU_B_BYTES + 256;
+constexpr uint32_t RU_PUSH_BYTES = (RU_CTAS - 1) * RU_B_KB_BYTES;         // what the 7 peers deliver per step
+constexpr int RU_TMEM_COLS = 64;
+
+__global__ void __cluster_dims__(RU_CTAS, 1, 1) __launch_bounds__(RU_THREADS, 1)
+rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
+                const float* __restrict__ gi, __half* __restrict__ hs_hi, __half* __restrict__ hs_lo,
+                const float* __restrict__ acc_scale, int B, int L, unsigned long long* tbuf) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
+    uint8_t* sA = smem;                                    // [8 kb][128 stacked rows x 128 B]
+    uint8_t* sB = smem + RU_A_BYTES;                       // [2 parities][8 kb][48 stacked rows x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RU_A_BYTES + 2 * RU_B_BYTES);
+    uint64_t* w_full = bars;                               // W_hh slice landed
+    uint64_t* h_full = bars + 1;                           // [2] h_t complete in a parity buffer (local arrive + 7 pushes)
+    uint64_t* acc_full = bars + 3;                         // MMAs of the step retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int n_clusters = gridDim.x / RU_CTAS, cluster_id = blockIdx.x / RU_CTAS;
+    const uint32_t sB_s = ptx::smem_u32(sB);
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&mapW_hi); ptx::prefetch_tmap(&mapW_lo);
+        ptx::mbar_init(w_full, 1);
+        ptx::mbar_init(&h_full[0], 1);
+        ptx::mbar_init(&h_full[1], 1);
+        ptx::mbar_init(acc_full, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 0) ptx::tmem_alloc(tmem_slot, RU_TMEM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) {
+        // resident A operand.  Stacked row order of a k-block: for q = 0..3: 16 hi rows then 16 lo rows of
+        // units 16q..16q+15, so both partial rows of a unit sit in the same TMEM lane quarter.
+        ptx::mbar_expect_tx(w_full, RU_A_BYTES);
+        for (int kb = 0; kb < 8; ++kb)
+            for (int q = 0; q < 4; ++q) {
+                uint8_t* dst = sA + kb * RU_A_KB_BYTES + q * 32 * 128;
+                ptx::tma_load_2d(dst, &mapW_hi, w_full, kb * 64, (int)rank * RU_UNITS + q * 16);
+                ptx::tma_load_2d(dst + 16 * 128, &mapW_lo, w_full, kb * 64, (int)rank * RU_UNITS + q * 16);
+            }
+    }
+    cluster_arrive();          // every CTA's barriers are initialised before any peer pushes into it
+    cluster_wait();
+
+    uint32_t hpar0 = 0, hpar1 = 0; // phase parities of h_full[0/1] (MMA issuer)
+    uint32_t apar = 0;             // phase parity of acc_full (epilogue threads)
+
+    for (int rb = cluster_id; rb * RU_N < B; rb += n_clusters) {
+        const int b0 = rb * RU_N;
+        if (warp == 0) {
+            // ================= MMA issuer =================
+            if (lane == 0) {
+                constexpr uint32_t idesc = umma_idesc_f16(2 * RU_UNITS, 2 * RU_N);
+                ptx::mbar_wait(w_full, 0);                 // completes once; later waits return immediately
+                const uint32_t a0 = ptx::smem_u32(sA);
+                for (int t = 1; t < L; ++t) {              // step 0 has h = 0: no product
+                    const int cur = t & 1;
+                    if (cur) { ptx::mbar_wait(&h_full[1], hpar1); hpar1 ^= 1; }
+                    else     { ptx::mbar_wait(&h_full[0], hpar0); hpar0 ^= 1; }
+                    if (tbuf && blockIdx.x == 0 && (t == 20 || t == 21)) tbuf[(t - 20) * 4 + 0] = ptx::globaltimer_ns();
+                    ptx::tc_fence_after();
+                    const uint32_t bb = sB_s + (uint32_t)cur * RU_B_BYTES;
+#pragma unroll
+                    for (int kb = 0; kb < 8; ++kb) {
+                        const uint64_t ad = umma_smem_desc(a0 + kb * RU_A_KB_BYTES);
+                        const uint64_t bd = umma_smem_desc(bb + kb * RU_B_KB_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            ptx::umma_f16(tmem_base, ad + adv, bd + adv, idesc, (kb | k) ? 1u : 0u);
+                        }
+                    }
+                    ptx::umma_commit(acc_full);
+                    if (tbuf && blockIdx.x == 0 && t == 20) tbuf[1] = ptx::globaltimer_ns();
+                }
+            }
+        } else {
+            // ===== epilogue: warps 1..8; TMEM quarter = warp % 4, window half ch = (warp-1)/4 =====
+            const int q = warp & 3;
+            const int ch = (warp - 1) >> 2;
+            const int lh = lane >> 4;                            // 0: hi-row lane, 1: lo-row lane of the same unit
+            const int ul = q * 16 + (lane & 15);                 // unit within the CTA
+            const int unit = (int)rank * RU_UNITS + ul;
+            const int nb = 12 * ch + 6 * lh;                     // first of the 6 windows this lane finishes
+            const float asc = __ldg(acc_scale);                  // 1 / (s_w * 16)
+            const int et = (int)threadIdx.x - 32;                // 0..255 among the epilogue threads
+            for (int t = 0; t < L; ++t) {
+                const int nxt = (t + 1) & 1;
+                float g[6];                                      // gi of this lane's outputs (latency overlaps the MMA wait)
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                    g[j] = __ldg(gi + ((size_t)min(b0 + nb + j, B - 1) * L + t) * R + unit);
+                float pre[6];
+                if (t > 0) {
+                    ptx::mbar_wait(acc_full, apar);
+                    apar ^= 1;
+                    if (tbuf && blockIdx.x == 0 && t == 20 && et == 0) tbuf[2] = ptx::globaltimer_ns();
+                    ptx::tc_fence_after();
+                    // columns [12ch, 12ch+12) (x h_hi) and [24+12ch, ...) (x h_lo) of this lane's stacked row
+                    uint32_t r0[12], r1[12];
+                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(12 * ch);
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]) : "r"(ta) : "memory");
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                 : "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]), "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11])
+                                 : "r"(ta + 4) : "memory");
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]) : "r"(ta + 24) : "memory");
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                 : "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]), "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11])
+                                 : "r"(ta + 28) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    ptx::tc_fence_before();
+                    float s[12];
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) s[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                    // fold the hi-row and lo-row lanes of a unit; lane half lh keeps windows 6lh..6lh+5
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const float mine = lh ? s[j + 6] : s[j];
+                        const float send = lh ? s[j] : s[j + 6];
+                        pre[j] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) pre[j] = 0.f;
+                }
+                // h_t -> this CTA's k-block of the next B operand (swizzled rows: windows hi, then windows lo)
+                uint8_t* tile = sB + nxt * RU_B_BYTES + (int)rank * RU_B_KB_BYTES;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int n = nb + j;
+                    const float h = tanhf(fmaf(pre[j], asc, g[j]));
+                    __half hi, lo;
+                    half_split(h * ACT_SCALE, hi, lo);
+                    const int off = ((((ul >> 3) ^ (n & 7))) << 4) + (ul & 7) * 2;       // (24 + n) & 7 == n & 7
+                    *reinterpret_cast<__half*>(tile + n * 128 + off) = hi;
+                    *reinterpret_cast<__half*>(tile + (RU_N + n) * 128 + off) = lo;
+                }
+                ptx::fence_async_smem();                              // generic writes -> async proxy (MMA, bulk copies)
+                asm volatile("bar.sync 1, 256;" ::: "memory");        // the whole k-block is written
+                if (tbuf && blockIdx.x == 0 && t == 20 && et == 0) tbuf[3] = ptx::globaltimer_ns();
+                if (t + 1 < L) {
+                    // publish: local arrival + the 7 peers' bytes complete h_full[nxt] in every CTA
+                    if (et == 32) ptx::mbar_expect_tx(&h_full[nxt], RU_PUSH_BYTES);
+                    if (et < RU_CTAS && (uint32_t)et != rank) {
+                        const uint32_t src = ptx::smem_u32(tile);
+                        dsmem_bulk_push(map_to_cta(src, (uint32_t)et), src, RU_B_KB_BYTES,
+                                        map_to_cta(ptx::smem_u32(&h_full[nxt]), (uint32_t)et));
+                    }
+                }
+                // hs[b, t, 64c .. 64c+63] (hi / lo planes) from the tile: 16-byte chunks, un-swizzled
+                for (int i = et; i < 2 * RU_N * 8; i += 32 * RU_EPI_WARPS) {
+                    const int row = i >> 3, pc = i & 7, lc = pc ^ (row & 7);
+                    const int plane = row >= RU_N, n = row - plane * RU_N;
+                    if (b0 + n < B) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(tile + row * 128 + pc * 16);
+                        __half* dst = (plane ? hs_lo : hs_hi) + ((size_t)(b0 + n) * L + t) * R + rank * RU_UNITS + lc * 8;
+                        *reinterpret_cast<uint4*>(dst) = v;
+                    }
+                }
+                // the tile of parity nxt is rewritten two steps later; by then every peer has consumed this
+                // push (it had to, to produce the h this CTA waits for) and the loop above has finished
+            }
+        }
+        // next row block reuses both h buffers: every CTA must have finished its last MMAs / reads
+        __syncthreads();
+        cluster_arrive();
+        cluster_wait();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, RU_TMEM_COLS);
+    }
+}
+
+}  // namespace tip

@@ -575,6 +575,7 @@ struct UmmaMaps {
     UmmaOperand a_xin, a_xa, a_xb, a_att, a_hid, a_hs;                    // activations (box 32 x 128)
     UmmaOperand w_in, w_qkv[MAX_LAYERS], w_o[MAX_LAYERS], w_1[MAX_LAYERS], w_2[MAX_LAYERS], w_ih, w_l;
     UmmaOutput o_xa, o_xb, o_hid, o_qkv, o_gi;                             // TMA-store targets
+    UmmaOperand w_hh;                                                      // resident A operand of the recurrence (box 64 x 64)
     int num_sms = 148;
     bool attrs_set = false;
 };
@@ -667,6 +668,7 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         wgt(mp.w_2[l], L.w2_hi, L.w2_lo, E, F, 256);
     }
     if (d.with_rnn) wgt(mp.w_ih, o.wih_hi, o.wih_lo, R, E, 128);
+    if (d.with_rnn) wgt(mp.w_hh, o.whh_hi, o.whh_lo, R, R, 16);     // 16-row boxes: hi/lo rows interleave per TMEM quarter
     wgt(mp.w_l, o.wl_hi, o.wl_lo, HEAD_NPAD, d.khead, 128);
     if (!ok) { err = "cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor-map arguments)"; return TIP_ERR_CUDA; }
     int dev = 0;
