@@ -9,6 +9,7 @@
 #include "tip_simt.cuh"
 #include "tip_umma.cuh"
 #include "tip_rnn_umma.cuh"
+#include "tip_attn_mma.cuh"
 
 using namespace tip;
 
@@ -397,6 +398,16 @@ static void launch_sgemm(tip_model* m, cudaStream_t st, const float* A, int lda,
 
 static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, float* out, float* out_lo,
                              int B, int L, float drop_p, uint64_t seed) {
+    if (out_lo) {
+        // tcgen05 engine: qkv and the output are FP16 hi/lo planes; warp-level tensor-core kernel
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES); attr = true; }
+        const __half* qh = reinterpret_cast<const __half*>(qkv);
+        attention_mma_kernel<<<dim3(B, NH / AM_HPB), AM_HPB * 32, AM_SMEM_BYTES, st>>>(
+            qh, qh + (size_t)m->cap_rows * 3 * E, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), L, drop_p, seed);
+        m->launches++;
+        return;
+    }
     static const int akind = getenv("TIP_ATTN") ? atoi(getenv("TIP_ATTN")) : 0;
     if (B >= 32 && akind == 1) attention_kernel<4, 4><<<dim3(B, NH / 4), 320, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
     else if (B >= 32) attention_kernel<2, 4><<<dim3(B, NH / 4), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
@@ -534,6 +545,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
         const LayerOff& Lo = o.layer[l];
         mark(m, st, "qkv", l);
         ep = Epi{}; ep.bias = W + Lo.bqkv; ep.out = m->qkv; ep.ldc = 3 * E;
+        if (umma) ep.out_lo = m->qkv + (size_t)m->cap_rows * 3 * E / 2;     // FP16 planes for the mma attention
         gemm(UG_QKV, l, m->xa, E, W + Lo.wqkv, 3 * E, ep, false);
         mark(m, st, "attention", l);
         launch_attention(m, st, m->qkv, m->att, lo_att, B, L, p_enc, seed + 101 * (l + 1));

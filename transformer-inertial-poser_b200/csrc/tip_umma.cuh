@@ -642,7 +642,7 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
     outp(mp.o_xa, xa, plane_e, E, true);
     outp(mp.o_xb, xb, plane_e, E, true);
     outp(mp.o_hid, hid, plane_f, F, true);
-    outp(mp.o_qkv, qkv, 0, 3 * E, false);
+    outp(mp.o_qkv, qkv, (size_t)cap_rows * 3 * E, 3 * E, true);      // FP16 hi/lo planes of 16*q|k|v for the mma attention
     outp(mp.o_gi, gi, 0, R, false);
     // activation planes: hi at the start of the buffer, lo `plane` halves later (same bytes as one fp32 plane)
     auto act = [&](UmmaOperand& op, const float* p, size_t plane, int cols) {
