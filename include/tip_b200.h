@@ -123,6 +123,14 @@ int  tip_stream_reset(tip_model* m, int n_streams);
 int  tip_stream_step(tip_model* m, const float* imu_row, const float* s_row, float* y_last,
                      int rows_on_host, const tip_dropout* drop, void* stream);
 int  tip_stream_length(const tip_model* m);   /* current L (0 before the first push) */
+/* Row N1: the same step fed with RAW IMU frames (S, 72) = 6 global rotations (54) + 6 global
+ * accelerations (18) as RTRunnerMin.step receives them (real_time_runner_minimal.py:118).  The runner's
+ * record_raw_imu (:59-76: 5-frame rotation delay, 11-frame acceleration mean), imu_rotate_to_local
+ * (data_utils.py:190-219) and the 40-frame acc-sum / 15 feature (:134-141) run on the device; only the
+ * newest window row is computed.  *produced is 0 for the first 5 calls (the runner returns s_init then,
+ * :125-128; y_last is untouched) and 1 afterwards. */
+int  tip_stream_step_raw(tip_model* m, const float* raw_imu, const float* s_row, float* y_last,
+                         int rows_on_host, const tip_dropout* drop, void* stream, int* produced);
 
 /* ---- introspection -------------------------------------------------------------------------- */
 /* Algorithmic bytes / flops of one forward:

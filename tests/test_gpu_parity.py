@@ -217,3 +217,48 @@ def test_stochastic_mode_statistics():
     assert not torch.equal(y4, y5) and torch.isfinite(y4).all()
     m.eval()
     assert torch.equal(m(xi, xs).cpu(), y0)
+
+
+def _random_raw_imu(rs, T, S):
+    """(T, S, 72) raw frames: 6 proper rotation matrices (random walk) + 6 accelerations."""
+    from scipy.spatial.transform import Rotation as Rot
+    out = np.empty((T, S, 72), np.float64)
+    for s in range(S):
+        R = Rot.random(6, random_state=rs.randint(1 << 30))
+        for t in range(T):
+            R = Rot.from_rotvec(0.05 * rs.standard_normal((6, 3))) * R
+            out[t, s, :54] = R.as_matrix().reshape(-1)
+            out[t, s, 54:] = 3.0 * rs.standard_normal(18)
+    return out
+
+
+def test_raw_imu_preprocessing_on_device():
+    """Row N1: record_raw_imu + imu_rotate_to_local + acc-sum on the device vs the numpy restatement of
+    the runner (oracle.WindowAssembler), then the model on the assembled windows."""
+    sd = O.random_state_dict(29)
+    m = make_model(sd)
+    from tip_b200.streaming import StreamSession
+    S, T = 3, 70
+    rs = np.random.RandomState(7)
+    raw = _random_raw_imu(rs, T, S)
+    _, xs_all = O.synth_inputs(51, S, T, nan_frac=0.0)
+    sess = StreamSession(m, n_streams=S)
+    was = [O.WindowAssembler() for _ in range(S)]
+    n_out = 0
+    for t in range(T):
+        wins = [wa.push(raw[t, s]) for s, wa in enumerate(was)]
+        y = sess.step_raw(raw[t].astype(np.float32), xs_all[:, n_out])
+        if wins[0] is None:
+            assert y is None and t < 5
+            continue
+        assert y is not None
+        L = wins[0].shape[0]
+        dev_win = sess.window("win_imu").cpu().numpy()[:, :L]
+        ref_win = np.stack(wins).astype(np.float32)
+        assert np.abs(dev_win - ref_win).max() < 2e-5, (t, np.abs(dev_win - ref_win).max())
+        if t in (5, 6, 20, 44, 45, 69):
+            lo = n_out + 1 - L
+            ref = O.forward(sd, ref_win, xs_all[:, lo:n_out + 1])[:, -1]
+            assert np.abs(y - ref).max() < TOL, (t, np.abs(y - ref).max())
+        n_out += 1
+    assert n_out == T - 5 and sess.length == 40

@@ -53,6 +53,9 @@ struct tip_model {
     int n_streams = 0, stream_len = 0;
     float *win_imu = nullptr, *win_s = nullptr, *st_rows = nullptr, *st_ximu = nullptr,
           *st_xs = nullptr, *st_y = nullptr, *st_ylast = nullptr, *h_rows = nullptr, *h_ylast = nullptr;
+    float *raw_ring = nullptr, *st_raw = nullptr, *h_raw = nullptr;    // N1: raw-IMU pre-processing state
+    double* acc_ring = nullptr;
+    int n_raw = 0, n_rows = 0;
     cudaGraphExec_t st_graph = nullptr;   // captured steady-state step (L == MAXL)
     int st_graph_launches = 0;
 
@@ -162,7 +165,10 @@ extern "C" int tip_create(const tip_dims* dims, tip_model** out) {
 
 static void free_stream_state(tip_model* m) {
     if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
-    for (float** p : {&m->win_imu, &m->win_s, &m->st_rows, &m->st_ximu, &m->st_xs, &m->st_y, &m->st_ylast})
+    if (m->acc_ring) { cudaFree(m->acc_ring); m->acc_ring = nullptr; }
+    if (m->h_raw) { cudaFreeHost(m->h_raw); m->h_raw = nullptr; }
+    m->n_raw = m->n_rows = 0;
+    for (float** p : {&m->win_imu, &m->win_s, &m->st_rows, &m->st_ximu, &m->st_xs, &m->st_y, &m->st_ylast, &m->raw_ring, &m->st_raw})
         if (*p) { cudaFree(*p); *p = nullptr; }
     for (float** p : {&m->h_rows, &m->h_ylast})
         if (*p) { cudaFreeHost(*p); *p = nullptr; }
@@ -331,6 +337,8 @@ extern "C" int tip_debug_tensor(tip_model* m, const char* name, float* dst, int6
     else if (n == "qkv") { src = m->qkv; *numel = rows * 3 * E; }
     else if (n == "gi")  { src = m->gi;  *numel = rows * R; }
     else if (n == "hs")  { src = m->hs;  *numel = rows * R; }
+    else if (n == "win_imu") { src = m->win_imu; *numel = (int64_t)m->n_streams * MAXL * m->d.n_imu; }
+    else if (n == "win_s")   { src = m->win_s;   *numel = (int64_t)m->n_streams * MAXL * m->d.size_s; }
     else { m->set_error("tip_debug_tensor: unknown buffer " + n); return TIP_ERR_INVALID_ARG; }
     if (dst) {
         if (capacity < *numel || !src) { m->set_error("tip_debug_tensor: capacity too small"); return TIP_ERR_INVALID_ARG; }
@@ -668,6 +676,10 @@ extern "C" int tip_stream_reset(tip_model* m, int n_streams) {
     TIP_CUDA_TRY(m, cudaMalloc(&m->st_ylast, S * d.size_s * sizeof(float)));
     TIP_CUDA_TRY(m, cudaMallocHost(&m->h_rows, S * d.d_in * sizeof(float)));
     TIP_CUDA_TRY(m, cudaMallocHost(&m->h_ylast, S * d.size_s * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMalloc(&m->raw_ring, S * IMU_RING * IMU_RAW * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMalloc(&m->st_raw, S * IMU_RAW * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMalloc(&m->acc_ring, S * ACC_WIN * 18 * sizeof(double)));
+    TIP_CUDA_TRY(m, cudaMallocHost(&m->h_raw, S * IMU_RAW * sizeof(float)));
     TIP_CUDA_TRY(m, cudaMemset(m->win_imu, 0, S * MAXL * d.n_imu * sizeof(float)));
     TIP_CUDA_TRY(m, cudaMemset(m->win_s, 0, S * MAXL * d.size_s * sizeof(float)));
     m->n_streams = n_streams;
@@ -703,24 +715,11 @@ static int stream_step_device(tip_model* m, const tip_dropout* drop, cudaStream_
     return TIP_OK;
 }
 
-extern "C" int tip_stream_step(tip_model* m, const float* imu_row, const float* s_row, float* y_last,
-                               int rows_on_host, const tip_dropout* drop, void* stream_) {
-    if (!m || !imu_row || !s_row || !y_last) return TIP_ERR_INVALID_ARG;
-    if (!m->packed) { m->set_error("tip_stream_step before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
-    if (m->n_streams < 1) { m->set_error("tip_stream_step before tip_stream_reset"); return TIP_ERR_INVALID_ARG; }
-    cudaStream_t st = (cudaStream_t)stream_;
-    TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+// device + completion part of one streaming step; st_rows already holds (imu rows | s rows)
+static int stream_step_core(tip_model* m, float* y_last, int rows_on_host, const tip_dropout* drop, cudaStream_t st) {
     const Dims& d = m->d;
     const size_t S = m->n_streams;
-    const size_t n_i = S * d.n_imu, n_s = S * d.size_s;
-    if (rows_on_host) {
-        memcpy(m->h_rows, imu_row, n_i * sizeof(float));
-        memcpy(m->h_rows + n_i, s_row, n_s * sizeof(float));
-        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows, m->h_rows, (n_i + n_s) * sizeof(float), cudaMemcpyHostToDevice, st));
-    } else {
-        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows, imu_row, n_i * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows + n_i, s_row, n_s * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    }
+    const size_t n_s = S * d.size_s;
     const int len_before = m->stream_len;
     const bool stochastic = drop && (drop->in_dropout > 0.f || drop->past_state_dropout > 0.f || drop->encoder_dropout > 0.f);
     const bool steady = (len_before == MAXL);
@@ -767,4 +766,59 @@ extern "C" int tip_stream_step(tip_model* m, const float* imu_row, const float* 
         TIP_CUDA_TRY(m, cudaMemcpyAsync(y_last, m->st_ylast, n_s * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     return TIP_OK;
+}
+
+extern "C" int tip_stream_step(tip_model* m, const float* imu_row, const float* s_row, float* y_last,
+                               int rows_on_host, const tip_dropout* drop, void* stream_) {
+    if (!m || !imu_row || !s_row || !y_last) return TIP_ERR_INVALID_ARG;
+    if (!m->packed) { m->set_error("tip_stream_step before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
+    if (m->n_streams < 1) { m->set_error("tip_stream_step before tip_stream_reset"); return TIP_ERR_INVALID_ARG; }
+    cudaStream_t st = (cudaStream_t)stream_;
+    TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    const Dims& d = m->d;
+    const size_t S = m->n_streams;
+    const size_t n_i = S * d.n_imu, n_s = S * d.size_s;
+    if (rows_on_host) {
+        memcpy(m->h_rows, imu_row, n_i * sizeof(float));
+        memcpy(m->h_rows + n_i, s_row, n_s * sizeof(float));
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows, m->h_rows, (n_i + n_s) * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows, imu_row, n_i * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows + n_i, s_row, n_s * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    return stream_step_core(m, y_last, rows_on_host, drop, st);
+}
+
+// Row N1: push RAW IMU frames (S, 72) -- the runner's record_raw_imu + window features run on the device.
+// *produced = 0 during the first 5 calls (no smoothed frame yet, the runner returns s_init); then 1.
+extern "C" int tip_stream_step_raw(tip_model* m, const float* raw_imu, const float* s_row, float* y_last,
+                                   int rows_on_host, const tip_dropout* drop, void* stream_, int* produced) {
+    if (!m || !raw_imu || !s_row || !y_last || !produced) return TIP_ERR_INVALID_ARG;
+    if (!m->packed) { m->set_error("tip_stream_step_raw before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
+    if (m->n_streams < 1) { m->set_error("tip_stream_step_raw before tip_stream_reset"); return TIP_ERR_INVALID_ARG; }
+    cudaStream_t st = (cudaStream_t)stream_;
+    TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    const Dims& d = m->d;
+    const size_t S = m->n_streams;
+    const size_t n_i = S * d.n_imu, n_s = S * d.size_s, n_r = S * IMU_RAW;
+    if (rows_on_host) {
+        memcpy(m->h_raw, raw_imu, n_r * sizeof(float));
+        memcpy(m->h_rows + n_i, s_row, n_s * sizeof(float));
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_raw, m->h_raw, n_r * sizeof(float), cudaMemcpyHostToDevice, st));
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows + n_i, m->h_rows + n_i, n_s * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_raw, raw_imu, n_r * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows + n_i, s_row, n_s * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    imu_push_kernel<<<(unsigned)S, 32, 0, st>>>(m->st_raw, m->raw_ring, m->acc_ring, m->st_rows, d.n_imu, m->n_raw, m->n_rows);
+    TIP_CUDA_TRY(m, cudaGetLastError());
+    m->n_raw += (m->n_raw == 0) ? IMU_DELAY + 1 : 1;
+    if (m->n_raw < IMU_RING) {
+        *produced = 0;
+        if (rows_on_host) TIP_CUDA_TRY(m, cudaStreamSynchronize(st));
+        return TIP_OK;
+    }
+    m->n_rows += 1;
+    *produced = 1;
+    return stream_step_core(m, y_last, rows_on_host, drop, st);
 }

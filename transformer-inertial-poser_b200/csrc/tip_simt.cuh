@@ -671,6 +671,82 @@ window_push_kernel(float* __restrict__ win, const float* __restrict__ new_row, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row N1 of SURVEY.md 8f -- the runner's per-frame IMU pre-processing on the device
+// (real_time_runner_minimal.py:59-76 record_raw_imu, :131-141 window features; data_utils.py:190-219
+// imu_rotate_to_local; constants.py:15-18):
+//   raw (72,) = 6 global rotations (54) + 6 global accelerations (18), appended to an 11-frame ring
+//   (the very first frame is replicated 5 extra times, :60-63).  Once 11 raw frames exist, the new
+//   model row is  [R_root | R_root^-1 R_i (5) | a_root | R_root^-1 a_i (5) | acc-sum / 15]  with the
+//   rotations taken from 5 frames ago, the accelerations averaged over the 11 raw frames, and acc-sum =
+//   sum of the rotated accelerations of the last <= 40 rows.  The reference keeps these buffers in
+//   float64 and casts the window to float32; the arithmetic here is done in double for the same
+//   rounding.  One CTA (one warp) per stream; rows already written never change, so only the newest
+//   row is produced (the reference recomputes the whole window every frame).
+constexpr int IMU_RAW = 72, IMU_RING = 11, IMU_DELAY = 5, ACC_WIN = 40;
+__global__ void __launch_bounds__(32)
+imu_push_kernel(const float* __restrict__ raw_new, float* __restrict__ raw_ring, double* __restrict__ acc_ring,
+                float* __restrict__ row_out, int n_imu, int n_raw_before, int n_rows_before) {
+    const int s = blockIdx.x, lane = threadIdx.x;
+    float* ring = raw_ring + (size_t)s * IMU_RING * IMU_RAW;
+    double* aring = acc_ring + (size_t)s * ACC_WIN * 18;
+    const float* nr = raw_new + (size_t)s * IMU_RAW;
+    // append (first frame: 5 pads + itself)
+    const int n_app = n_raw_before == 0 ? IMU_DELAY + 1 : 1;
+    for (int a = 0; a < n_app; ++a)
+        for (int c = lane; c < IMU_RAW; c += 32) ring[((n_raw_before + a) % IMU_RING) * IMU_RAW + c] = nr[c];
+    __syncwarp();
+    const int n_raw = n_raw_before + n_app;
+    if (n_raw < IMU_RING) return;                              // no smoothed frame yet (runner :125-128)
+    __shared__ double sm[IMU_RAW];                             // smoothed frame: rotations (54) + mean accelerations (18)
+    const float* rot_src = ring + ((n_raw - 1 - IMU_DELAY) % IMU_RING) * IMU_RAW;     // raw[-IMU_n_smooth - 1]
+    for (int c = lane; c < 54; c += 32) sm[c] = (double)rot_src[c];
+    if (lane < 18) {
+        double acc = 0.0;
+        for (int k = 0; k < IMU_RING; ++k)                     // chronological, like np.mean over axis 0
+            acc += (double)ring[((n_raw - IMU_RING + k) % IMU_RING) * IMU_RAW + 54 + lane];
+        sm[54 + lane] = acc / (double)IMU_RING;
+    }
+    __syncwarp();
+    // inverse of the root rotation (np.linalg.inv, data_utils.py:196): adjugate / determinant
+    double r[9], inv[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r[i] = sm[i];
+    inv[0] = r[4] * r[8] - r[5] * r[7]; inv[1] = r[2] * r[7] - r[1] * r[8]; inv[2] = r[1] * r[5] - r[2] * r[4];
+    inv[3] = r[5] * r[6] - r[3] * r[8]; inv[4] = r[0] * r[8] - r[2] * r[6]; inv[5] = r[2] * r[3] - r[0] * r[5];
+    inv[6] = r[3] * r[7] - r[4] * r[6]; inv[7] = r[1] * r[6] - r[0] * r[7]; inv[8] = r[0] * r[4] - r[1] * r[3];
+    const double det = r[0] * inv[0] + r[1] * inv[3] + r[2] * inv[6];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) inv[i] /= det;
+    float* out = row_out + (size_t)s * n_imu;
+    double* anew = aring + (n_rows_before % ACC_WIN) * 18;
+    // 72 outputs: [0:9] root R, [9:54] inv*R_i, [54:57] root acc, [57:72] inv*a_i
+    for (int c = lane; c < IMU_RAW; c += 32) {
+        double v;
+        if (c < 9) v = sm[c];
+        else if (c < 54) {
+            const int i = (c - 9) / 9, e = (c - 9) % 9, rr = e / 3, cc = e % 3;
+            const double* Ri = sm + 9 + 9 * i;
+            v = inv[rr * 3 + 0] * Ri[0 * 3 + cc] + inv[rr * 3 + 1] * Ri[1 * 3 + cc] + inv[rr * 3 + 2] * Ri[2 * 3 + cc];
+        } else if (c < 57) v = sm[c];
+        else {
+            const int i = (c - 57) / 3, rr = (c - 57) % 3;
+            const double* ai = sm + 57 + 3 * i;
+            v = inv[rr * 3 + 0] * ai[0] + inv[rr * 3 + 1] * ai[1] + inv[rr * 3 + 2] * ai[2];
+        }
+        out[c] = (float)v;
+        if (c >= 54) anew[c - 54] = v;
+    }
+    __syncwarp();
+    if (n_imu > IMU_RAW && lane < 18) {                        // acc-sum feature (:134-141), /ACC_SUM_DOWN_SCALE
+        const int cnt = min(n_rows_before + 1, ACC_WIN);
+        double acc = 0.0;
+        for (int k = 0; k < cnt; ++k)                          // chronological over the last <= 40 rows
+            acc += aring[((n_rows_before + 1 - cnt + k) % ACC_WIN) * 18 + lane];
+        out[IMU_RAW + lane] = (float)(acc / 15.0);
+    }
+}
+
 // gather compacted (S, L, width) windows out of the (S, MAXL, width) storage when L < MAXL
 __global__ void window_compact_kernel(const float* __restrict__ win, float* __restrict__ out,
                                       int S, int L, int width) {

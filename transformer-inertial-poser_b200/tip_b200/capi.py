@@ -49,6 +49,8 @@ SIGNATURES = {
     "tip_stream_reset": (C.c_int, [_VP, C.c_int]),
     "tip_stream_step": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.POINTER(TipDropout), _VP]),
     "tip_stream_length": (C.c_int, [_VP]),
+    "tip_stream_step_raw": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.POINTER(TipDropout), _VP,
+                                      C.POINTER(C.c_int)]),
     "tip_algorithmic_cost": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double)]),
     "tip_last_launch_count": (C.c_int, [_VP]),

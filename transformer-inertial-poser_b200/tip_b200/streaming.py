@@ -62,3 +62,43 @@ class StreamSession:
                                            C.byref(drop) if drop else None, C.c_void_p(stream))
         capi.check(self._lib, h, rc, "tip_stream_step")
         return y
+
+    def step_raw(self, raw_imu, s_row):
+        """Row N1: push RAW IMU frames (S, 72) = 6 global rotations + 6 global accelerations exactly as
+        ``RTRunnerMin.step`` receives ``cur_imu`` (real_time_runner_minimal.py:118); smoothing, root-local
+        rotation and the acc-sum feature run on the device.  Returns None for the first 5 calls (the
+        runner returns ``s_init`` then, :125-128), afterwards ``y[:, L-1, :]`` like ``step``."""
+        m = self.model
+        h = m._ensure(self.device)
+        S = self.n_streams
+        on_host = not (isinstance(raw_imu, torch.Tensor) and raw_imu.is_cuda)
+        if on_host:
+            xi = np.ascontiguousarray(np.asarray(raw_imu, dtype=np.float32).reshape(S, 72))
+            xs = np.ascontiguousarray(np.asarray(s_row, dtype=np.float32).reshape(S, m._size_s))
+            y = np.empty((S, m._size_s), dtype=np.float32)
+            pi, ps, py = xi.ctypes.data, xs.ctypes.data, y.ctypes.data
+        else:
+            xi = raw_imu.detach().to(torch.float32).contiguous().view(S, 72)
+            xs = s_row.detach().to(device=self.device, dtype=torch.float32).contiguous().view(S, m._size_s)
+            y = torch.empty((S, m._size_s), dtype=torch.float32, device=self.device)
+            pi, ps, py = xi.data_ptr(), xs.data_ptr(), y.data_ptr()
+        drop = m._dropout_struct()
+        produced = C.c_int(0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self._lib.tip_stream_step_raw(h, pi, ps, py, int(on_host), C.byref(drop) if drop else None,
+                                               C.c_void_p(stream), C.byref(produced))
+        capi.check(self._lib, h, rc, "tip_stream_step_raw")
+        return y if produced.value else None
+
+    def window(self, which="win_imu"):
+        """Copy of the device-resident windows (test hook): (S, 40, 72|90) or (S, 40, size_s)."""
+        m = self.model
+        n = C.c_int64()
+        capi.check(self._lib, self._h, self._lib.tip_debug_tensor(self._h, which.encode(), None, 0, C.byref(n), None),
+                   "tip_debug_tensor")
+        out = torch.empty(n.value, dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        capi.check(self._lib, self._h, self._lib.tip_debug_tensor(self._h, which.encode(), out.data_ptr(), n.value,
+                                                                  C.byref(n), C.c_void_p(stream)), "tip_debug_tensor")
+        return out.view(self.n_streams, 40, -1)
