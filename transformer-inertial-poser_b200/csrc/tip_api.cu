@@ -517,7 +517,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
     m->st_layers.clear();
     mark(m, st, "condition");
     {
-        const int64_t total = (int64_t)M * d.kin_pad;
+        const int64_t total = (int64_t)M * (d.kin_pad / 8);
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
         condition_kernel<<<blocks, 256, 0, st>>>(x_imu, x_s, keep_mask, past_scale, m->xin, lo_xin, M, d.n_imu,
                                                  d.size_s, d.kin_pad, p_in, p_past, seed);

@@ -12,37 +12,53 @@ namespace tip {
 // dropout(in_dropout) on x_imu, zero root velocity (also folded into the packed weight),
 // dropout(past_state_dropout) on x_s -- or an explicit keep-mask -- and the concat, written as
 // one (M, kin_pad) matrix (zero padded) in fp32 or TF32 hi/lo planes.
+__device__ __forceinline__ float condition_value(const float* __restrict__ x_imu, const float* __restrict__ x_s,
+                                                 const float* __restrict__ keep_mask, float past_scale, int r, int c,
+                                                 int n_imu, int size_s, int kin_pad, float p_in, float p_past,
+                                                 float inv_in, float inv_past, uint64_t seed) {
+    float v = 0.f;
+    const int64_t i = (int64_t)r * kin_pad + c;
+    if (c < n_imu) {
+        v = __ldg(x_imu + (int64_t)r * n_imu + c);
+        if (p_in > 0.f) v *= dropout_factor(p_in, inv_in, seed ^ 0x1111, i);
+    } else if (c < n_imu + size_s) {
+        const int cs = c - n_imu;
+        v = __ldg(x_s + (int64_t)r * size_s + cs);
+        if (v != v) v = 0.f;                               // :65  x_s[isnan] = 0
+        if (cs >= 108 && cs < 111) v = 0.f;                // :75  root velocity removed
+        if (keep_mask != nullptr) v *= __ldg(keep_mask + (int64_t)r * size_s + cs) * past_scale;
+        else if (p_past > 0.f) v *= dropout_factor(p_past, inv_past, seed ^ 0x2222, i);   // :77
+    }
+    return v;
+}
+// one thread produces 8 consecutive columns of a row (kin_pad is a multiple of 64): 16-byte stores into
+// the FP16 hi/lo planes (scale 1: raw model input) of the tcgen05 engine, or fp32 for the FFMA engine
 __global__ void condition_kernel(const float* __restrict__ x_imu, const float* __restrict__ x_s,
                                  const float* __restrict__ keep_mask, float past_scale,
                                  float* __restrict__ out, float* __restrict__ out_lo,
                                  int M, int n_imu, int size_s, int kin_pad,
                                  float p_in, float p_past, uint64_t seed) {
-    const int64_t total = (int64_t)M * kin_pad;
+    const int groups = kin_pad >> 3;
+    const int64_t total = (int64_t)M * groups;
     const float inv_in = p_in > 0.f ? 1.f / (1.f - p_in) : 1.f;
     const float inv_past = p_past > 0.f ? (p_past < 1.f ? 1.f / (1.f - p_past) : 0.f) : 1.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i / kin_pad);
-        const int c = (int)(i - (int64_t)r * kin_pad);
-        float v = 0.f;
-        if (c < n_imu) {
-            v = x_imu[(int64_t)r * n_imu + c];
-            if (p_in > 0.f) v *= dropout_factor(p_in, inv_in, seed ^ 0x1111, i);
-        } else if (c < n_imu + size_s) {
-            const int cs = c - n_imu;
-            v = x_s[(int64_t)r * size_s + cs];
-            if (v != v) v = 0.f;                               // :65  x_s[isnan] = 0
-            if (cs >= 108 && cs < 111) v = 0.f;                // :75  root velocity removed
-            if (keep_mask != nullptr) v *= keep_mask[(int64_t)r * size_s + cs] * past_scale;
-            else if (p_past > 0.f) v *= dropout_factor(p_past, inv_past, seed ^ 0x2222, i);   // :77
-        }
-        if (out_lo != nullptr) {          // FP16 hi/lo planes (scale 1: raw model input) for the tcgen05 engine
-            __half hi, lo;
-            half_split(v, hi, lo);
-            reinterpret_cast<__half*>(out)[i] = hi;
-            reinterpret_cast<__half*>(out_lo)[i] = lo;
+    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(gi / groups);
+        const int c0 = (int)(gi - (int64_t)r * groups) << 3;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            v[j] = condition_value(x_imu, x_s, keep_mask, past_scale, r, c0 + j, n_imu, size_s, kin_pad, p_in, p_past,
+                                   inv_in, inv_past, seed);
+        const int64_t o = (int64_t)r * kin_pad + c0;
+        if (out_lo != nullptr) {
+            half_split_store4(reinterpret_cast<__half*>(out) + o, reinterpret_cast<__half*>(out_lo) + o,
+                              make_float4(v[0], v[1], v[2], v[3]));
+            half_split_store4(reinterpret_cast<__half*>(out) + o + 4, reinterpret_cast<__half*>(out_lo) + o + 4,
+                              make_float4(v[4], v[5], v[6], v[7]));
         } else {
-            out[i] = v;
+            *reinterpret_cast<float4*>(out + o) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(out + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
     }
 }

@@ -407,6 +407,26 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                         }
                         __syncwarp();
                     }
+                } else if (!OUT_HALF && !(ep.drop_p > 0.f) && !(ep.dbg & 7)) {
+                    // fp32 output with arbitrary N / row pitch (the head: ldc = size_s = 131): lane <-> column,
+                    // one fully coalesced 128-byte row segment per store instruction
+#pragma unroll 1
+                    for (int c = 0; c < CH; ++c) {
+                        const int colb = n0 + half * (BN / 2) + c * 32;
+                        if (colb >= N) break;                                 // warp-uniform
+                        ptx::tmem_ld32(t_acc + c * 32, v);
+                        stg_write_row(stg, lane, v);
+                        __syncwarp();
+                        const int col = colb + lane;
+                        const float bv = col < N ? __ldg(ep.bias + col) : 0.f;
+                        const int nrow = min(32, M - rbase);
+#pragma unroll 4
+                        for (int r = 0; r < nrow; ++r) {
+                            const float x = reinterpret_cast<const float*>(stg_ptr(stg, r, lane >> 2))[lane & 3];
+                            if (col < N) ep.out[(size_t)(rbase + r) * ep.ldc + col] = fmaxf(fmaf(x, asc, bv), relu_floor);
+                        }
+                        __syncwarp();
+                    }
                 } else {
                     const float inv_keep = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
 #pragma unroll 1
