@@ -409,10 +409,21 @@ static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, fl
     if (out_lo) {
         // tcgen05 engine: qkv and the output are FP16 hi/lo planes; warp-level tensor-core kernel
         static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM_BYTES); attr = true; }
+        static const int hpb = getenv("TIP_ATTN_HPB") ? atoi(getenv("TIP_ATTN_HPB")) : 8;
+        if (!attr) {
+            cudaFuncSetAttribute(attention_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<8>::SMEM_BYTES);
+            cudaFuncSetAttribute(attention_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<4>::SMEM_BYTES);
+            cudaFuncSetAttribute(attention_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<2>::SMEM_BYTES);
+            attr = true;
+        }
         const __half* qh = reinterpret_cast<const __half*>(qkv);
-        attention_mma_kernel<<<dim3(B, NH / AM_HPB), AM_HPB * 32, AM_SMEM_BYTES, st>>>(
-            qh, qh + (size_t)m->cap_rows * 3 * E, reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(out_lo), L, drop_p, seed);
+        const __half* ql = qh + (size_t)m->cap_rows * 3 * E;
+        __half* oh = reinterpret_cast<__half*>(out);
+        __half* ol = reinterpret_cast<__half*>(out_lo);
+        // smaller CTAs (fewer heads each) quantise better over the SMs; the qkv pieces stay >= 64 bytes
+        if (hpb == 8)      attention_mma_kernel<8><<<dim3(B, NH / 8), 256, AttnCfg<8>::SMEM_BYTES, st>>>(qh, ql, oh, ol, L, drop_p, seed);
+        else if (hpb == 2) attention_mma_kernel<2><<<dim3(B, NH / 2), 64, AttnCfg<2>::SMEM_BYTES, st>>>(qh, ql, oh, ol, L, drop_p, seed);
+        else               attention_mma_kernel<4><<<dim3(B, NH / 4), 128, AttnCfg<4>::SMEM_BYTES, st>>>(qh, ql, oh, ol, L, drop_p, seed);
         m->launches++;
         return;
     }

@@ -18,12 +18,13 @@
 
 namespace tip {
 
-constexpr int AM_HPB = 8;                    // heads per CTA (one warp each)
-constexpr int AM_ROWB = AM_HPB * HD * 2 + 16; // bytes per row of a plane tile: 8 heads x 16 halves + 16 B pad (bank spread)
 constexpr int AM_VROWS = 48;                 // V rows (keys) padded to 3 k-steps of 16; rows >= L are zero
-constexpr int AM_QK_BYTES = MAXL * AM_ROWB;  // 10,880
-constexpr int AM_V_BYTES = AM_VROWS * AM_ROWB;               // 13,056
-constexpr int AM_SMEM_BYTES = 4 * AM_QK_BYTES + 2 * AM_V_BYTES;
+template <int HPB> struct AttnCfg {          // HPB heads per CTA (one warp each)
+    static constexpr int ROWB = HPB * HD * 2 + 16;          // bytes per row of a plane tile (+16 B pad: bank spread)
+    static constexpr int QK_BYTES = MAXL * ROWB;
+    static constexpr int V_BYTES = AM_VROWS * ROWB;
+    static constexpr int SMEM_BYTES = 4 * QK_BYTES + 2 * V_BYTES;
+};
 
 __device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -39,9 +40,12 @@ __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint3
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+template <int AM_HPB>
 __global__ void __launch_bounds__(AM_HPB * 32)
 attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict__ qkv_lo,
                      __half* __restrict__ out_hi, __half* __restrict__ out_lo, int L, float drop_p, uint64_t seed) {
+    constexpr int AM_ROWB = AttnCfg<AM_HPB>::ROWB, AM_QK_BYTES = AttnCfg<AM_HPB>::QK_BYTES, AM_V_BYTES = AttnCfg<AM_HPB>::V_BYTES;
+    constexpr int CPR = AM_HPB * 2;                  // 16-byte chunks per row of a plane tile
     extern __shared__ __align__(16) uint8_t am_smem[];
     uint8_t* sQh = am_smem;                          // [L][8 heads][16] halves
     uint8_t* sQl = sQh + AM_QK_BYTES;
@@ -57,16 +61,16 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
     const size_t rowbase = (size_t)b * L;
 
     // ---- stage Q, K, V rows with cp.async (16 B = 8 dims of one head); V rows L..47 are zeroed ----
-    for (int i = tid; i < L * 16 * 6; i += AM_HPB * 32) {          // (row, chunk 0..15, {Qh,Ql,Kh,Kl,Vh,Vl})
-        const int row = i / 96, r = i - row * 96, which = r >> 4, c = r & 15;
+    for (int i = tid; i < L * CPR * 6; i += AM_HPB * 32) {         // (row, {Qh,Ql,Kh,Kl,Vh,Vl}, chunk)
+        const int row = i / (6 * CPR), r = i - row * (6 * CPR), which = r / CPR, c = r - which * CPR;
         const __half* src = ((which & 1) ? qkv_lo : qkv_hi) + (rowbase + row) * (3 * E) + (which >> 1) * E + h0 * HD + c * 8;
         uint8_t* dst = (which == 0 ? sQh : which == 1 ? sQl : which == 2 ? sKh : which == 3 ? sKl : which == 4 ? sVh : sVl) +
                        row * AM_ROWB + c * 16;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int i = tid; i < (AM_VROWS - L) * 16 * 2; i += AM_HPB * 32) {
-        const int plane = i & 1, c = (i >> 1) & 15, row = L + (i >> 5);
+    for (int i = tid; i < (AM_VROWS - L) * CPR * 2; i += AM_HPB * 32) {
+        const int plane = i & 1, c = (i >> 1) % CPR, row = L + (i >> 1) / CPR;
         *reinterpret_cast<uint4*>((plane ? sVl : sVh) + row * AM_ROWB + c * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
