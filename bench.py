@@ -266,17 +266,21 @@ def main():
     ms_per_step = dev_ms / args.steps
     value = world * B * args.steps / (dev_ms / 1e3)
 
-    # ---- e2e: public call with pinned host buffers, H2D + forward + D2H per step ---------------
+    # ---- e2e: the C-ABI host-buffer entry (tip_forward_host through TF_RNN_Past_State.forward_host), i.e.
+    #      `model(x_imu.cuda(), x_s.cuda()).cpu()` of real_time_runner_minimal.py:149 with pinned host
+    #      buffers: H2D of the step's inputs + forward + D2H of the result + stream sync, every step -------
     hx = [(torch.from_numpy(synth(base_seed + 7000 + i, B)[0]).pin_memory(),
            torch.from_numpy(synth(base_seed + 7000 + i, B)[1]).pin_memory()) for i in range(2)]
+    hy = torch.empty((B, L_WIN, 131), dtype=torch.float32).pin_memory()
     for i in range(3):
-        model(hx[i % 2][0].cuda(non_blocking=True), hx[i % 2][1].cuda(non_blocking=True)).cpu()
+        model.forward_host(hx[i % 2][0], hx[i % 2][1], out=hy)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        y = model(hx[i % 2][0].to(dev, non_blocking=True), hx[i % 2][1].to(dev, non_blocking=True)).cpu()
+        y = model.forward_host(hx[i % 2][0], hx[i % 2][1], out=hy)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_check = float(y[0, -1, 0])          # the result is read on the host
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

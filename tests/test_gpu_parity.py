@@ -158,6 +158,24 @@ def test_forward_host_entry():
     assert yl.shape == (3, 131) and np.abs(yl - ref[:, -1]).max() < TOL
 
 
+def test_forward_host_pipelined_matches_device_call():
+    """B >= 64 takes the pipelined host entry (chunked H2D + conditioning, chunked head + D2H);
+    pinned and pageable buffers must give the device call's result bit for bit."""
+    sd = O.random_state_dict(30)
+    m = make_model(sd)
+    for B, L in ((256, 40), (70, 33), (64, 1)):
+        x_imu, x_s = O.synth_inputs(45, B, L)
+        y_dev = run(m, x_imu, x_s)
+        y_pageable = m.forward_host(x_imu, x_s).numpy()
+        out = torch.empty((B, L, 131)).pin_memory()
+        y_pinned = m.forward_host(torch.from_numpy(x_imu).pin_memory(), torch.from_numpy(x_s).pin_memory(), out=out)
+        assert y_pinned is out
+        np.testing.assert_array_equal(y_pageable, y_dev)
+        np.testing.assert_array_equal(out.numpy(), y_dev)
+    ref = O.forward(sd, x_imu, x_s)
+    assert np.abs(y_dev - ref).max() < TOL
+
+
 def test_repack_on_load_state_dict_and_param_update():
     sd_a, sd_b = O.random_state_dict(25), O.random_state_dict(26)
     m = make_model(sd_a)

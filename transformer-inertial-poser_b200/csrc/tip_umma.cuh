@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                  const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
                  const __grid_constant__ CUtensorMap mapC0, const __grid_constant__ CUtensorMap mapC1,
-                 int M, int N, int K, Epi ep) {
+                 int M, int N, int K, int m_tile0, int m_tile_cnt, Epi ep) {
     using Cfg = UmmaCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     // 128B-swizzled operand tiles need 1024-byte alignment.  The kernel has no static shared memory,
@@ -225,8 +225,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (N + BN - 1) / BN;
-    const int m_tiles = (M + UM_BM - 1) / UM_BM;
-    const int total_tiles = n_tiles * m_tiles;
+    const int total_tiles = n_tiles * m_tile_cnt;              // m-tiles [m_tile0, m_tile0 + m_tile_cnt)
     const int num_kb = K / UM_BK;
 
     if (warp == 0 && lane == 0) {
@@ -249,7 +248,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * UM_BM, n0 = (tile % n_tiles) * BN;
+                const int m0 = (m_tile0 + tile / n_tiles) * UM_BM, n0 = (tile % n_tiles) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
@@ -311,7 +310,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int m0 = (tile / n_tiles) * UM_BM, n0 = (tile % n_tiles) * BN;
+            const int m0 = (m_tile0 + tile / n_tiles) * UM_BM, n0 = (tile % n_tiles) * BN;
             const int rbase = m0 + quarter * 32;                  // first row of this warp
             // lean path: full tile, vector stores, no dropout (warp-uniform); everything else -> slow path
             const bool fast = (m0 + UM_BM <= M) && (n0 + BN <= N) && vec_ok && !(ep.drop_p > 0.f) && !(ep.dbg & 7);
@@ -704,7 +703,7 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
 }
 
 inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, const Epi& ep_in, bool ln,
-                      cudaStream_t st) {
+                      cudaStream_t st, int m_tile0 = 0, int m_tile_cnt = -1) {
     const UmmaOperand *A = nullptr, *B = nullptr;
     const UmmaOutput* C = nullptr;
     switch (which) {
@@ -721,19 +720,19 @@ inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, c
     ep.tma_out = (C && C->valid && !getenv("TIP_NO_TMA_STORE")) ? 1 : 0;
     const CUtensorMap& c0 = C ? C->c0 : A->hi;
     const CUtensorMap& c1 = C ? C->c1 : A->lo;
-    const int m_tiles = (M + UM_BM - 1) / UM_BM;
+    const int m_tiles = m_tile_cnt >= 0 ? m_tile_cnt : (M + UM_BM - 1) / UM_BM;
     if (ln) {
         const int tiles = m_tiles;                                // BN = 256 = the whole row
         umma_gemm_kernel<256, true, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<256>::SMEM_BYTES, st>>>(
-            A->hi, A->lo, B->hi, B->lo, c0, c1, M, N, K, ep);
+            A->hi, A->lo, B->hi, B->lo, c0, c1, M, N, K, m_tile0, m_tiles, ep);
     } else {
         const int tiles = m_tiles * ((N + 127) / 128);
         if (ep.out_lo)
             umma_gemm_kernel<128, false, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<128>::SMEM_BYTES, st>>>(
-                A->hi, A->lo, B->hi, B->lo, c0, c1, M, N, K, ep);
+                A->hi, A->lo, B->hi, B->lo, c0, c1, M, N, K, m_tile0, m_tiles, ep);
         else
             umma_gemm_kernel<128, false, false><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<128>::SMEM_BYTES, st>>>(
-                A->hi, A->lo, B->hi, B->lo, c0, c1, M, N, K, ep);
+                A->hi, A->lo, B->hi, B->lo, c0, c1, M, N, K, m_tile0, m_tiles, ep);
     }
 }
 

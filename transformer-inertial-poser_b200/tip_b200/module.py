@@ -220,19 +220,32 @@ class TF_RNN_Past_State(nn.Module):
         return y
 
     # ---- extras beyond the reference surface --------------------------------------------------
-    def forward_host(self, x_imu, x_s, last_row_only=False):
+    def forward_host(self, x_imu, x_s, last_row_only=False, out=None):
         """``model(x_imu.cuda(), x_s.cuda()).cpu()`` in one C call with host (numpy / CPU tensor)
         buffers: H2D, forward, D2H, stream sync (real_time_runner_minimal.py:149).  Runs on the
-        device the parameters live on."""
+        device the parameters live on.  Pinned buffers (``tensor.pin_memory()``) are used in place and,
+        for B >= 64, the copies are pipelined against the conditioning and head kernels; pageable
+        buffers go through the handle's pinned staging.  ``out``: optional pre-allocated CPU tensor."""
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("forward_host: move the module to a CUDA device first (.cuda())")
         h = self._ensure(dev)
         xi = torch.as_tensor(x_imu, dtype=torch.float32).contiguous()
         xs = torch.as_tensor(x_s, dtype=torch.float32).contiguous()
+        if xi.is_cuda or xs.is_cuda:
+            raise RuntimeError("forward_host takes host buffers; call the module itself with CUDA tensors")
+        if xi.dim() != 3 or xs.dim() != 3 or xi.shape[:2] != xs.shape[:2] or xi.shape[2] != self._n_imu \
+                or xs.shape[2] != self._size_s:
+            raise RuntimeError(f"expected x_imu (B,L,{self._n_imu}) and x_s (B,L,{self._size_s}), "
+                               f"got {tuple(xi.shape)} and {tuple(xs.shape)}")
         B, L = xi.shape[0], xi.shape[1]
-        y = torch.empty((B, self._size_s) if last_row_only else (B, L, self._size_s),
-                        dtype=torch.float32)
+        shape = (B, self._size_s) if last_row_only else (B, L, self._size_s)
+        if out is None:
+            y = torch.empty(shape, dtype=torch.float32)
+        else:
+            y = out
+            if y.is_cuda or y.dtype != torch.float32 or tuple(y.shape) != shape or not y.is_contiguous():
+                raise RuntimeError(f"forward_host: out must be a contiguous fp32 CPU tensor of shape {shape}")
         drop = self._dropout_struct()
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
