@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="windows per step per GPU")
-    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05 3xTF32")
+    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05 3xFP16 split")
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU-baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -335,8 +335,8 @@ def main():
     fwd_gbs = alg_bytes / (ms_per_step * 1e-3) / 1e9
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": ach_tf, "peak": tf_peak, "unit": "TFLOP/s",
-        "frac": ach_tf / tf_peak, "traffic": None, "peak_kind": f"{peak_kind} bf16 burst (cuBLAS); fp32-parity math is "
-        "3xTF32 so the reachable ceiling is peak/6",
+        "frac": ach_tf / tf_peak, "traffic": None, "peak_kind": f"{peak_kind} bf16 burst (cuBLAS); fp32-parity math is a "
+        "3-product FP16 split (3 MMAs per product), so the reachable ceiling is peak/3",
         "us_per_launch": per_launch[dom] * 1e3, "share_of_step": totals[dom] / tot_stage if tot_stage else None,
         "stage_us_per_forward": {k: round(v * 1e3, 2) for k, v in sorted(totals.items(), key=lambda kv: -kv[1])},
         "forward_hbm": {"bound": "hbm", "achieved": fwd_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -367,7 +367,7 @@ def main():
                                "nhid=1024 heads=16 (BASELINE configs[1]); replicas only",
                    "l2": "256 MiB memset between timed steps (outside the per-step event pair) + 4 rotating input sets",
                    "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks",
-                   "engine": {0: "auto", 1: "ffma", 2: "tcgen05-3xtf32"}[args.engine]},
+                   "engine": {0: "auto (tcgen05 3xFP16 split)", 1: "ffma", 2: "tcgen05-3xfp16"}[args.engine]},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,

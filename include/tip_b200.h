@@ -85,7 +85,7 @@ int  tip_num_weight_tensors(const tip_model* m);
 /* Mirrors load_state_dict + .cuda() (offline_testing_simple.py:96-97): takes DEVICE pointers to
  * the fp32 tensors in state-dict order, with their element counts (checked against the expected
  * shapes), and builds the private packed copy (head-permutation folded into in_linear rows,
- * root-velocity columns zeroed, 1/sqrt(d) folded into W_q/b_q, RNN biases pre-summed, TF32
+ * root-velocity columns zeroed, 1/sqrt(d) folded into W_q/b_q, RNN biases pre-summed, FP16
  * hi/lo splits).  Asynchronous on `stream`; the source tensors may be freed after the stream
  * has passed this point. */
 int  tip_pack_weights(tip_model* m, const float* const* tensors_dev, const int64_t* numels,

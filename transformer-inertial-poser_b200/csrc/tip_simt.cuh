@@ -11,7 +11,7 @@ namespace tip {
 // Input conditioning (reference simple_transformer_with_state.py:63-78): clone, NaN->0 on x_s,
 // dropout(in_dropout) on x_imu, zero root velocity (also folded into the packed weight),
 // dropout(past_state_dropout) on x_s -- or an explicit keep-mask -- and the concat, written as
-// one (M, kin_pad) matrix (zero padded) in fp32 or TF32 hi/lo planes.
+// one (M, kin_pad) matrix (zero padded) in fp32 or FP16 hi/lo planes.
 __device__ __forceinline__ float condition_value(const float* __restrict__ x_imu, const float* __restrict__ x_s,
                                                  const float* __restrict__ keep_mask, float past_scale, int r, int c,
                                                  int n_imu, int size_s, int kin_pad, float p_in, float p_past,

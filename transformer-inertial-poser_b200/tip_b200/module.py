@@ -256,7 +256,7 @@ class TF_RNN_Past_State(nn.Module):
         return y
 
     def set_gemm_engine(self, engine: int):
-        """0 auto, 1 FFMA fp32, 2 tcgen05 3xTF32 (tip_set_gemm_engine)."""
+        """0 auto (= 2), 1 FFMA fp32 cross-check kernels, 2 tcgen05 3xFP16-split kernels (tip_set_gemm_engine)."""
         dev = next(self.parameters()).device
         h = self._ensure(dev)
         capi.check(self._lib, h, self._lib.tip_set_gemm_engine(h, int(engine)), "tip_set_gemm_engine")
