@@ -191,6 +191,16 @@ def test_repack_on_load_state_dict_and_param_update():
     assert np.abs(yc - (yb + 1.0)).max() < 1e-5
 
 
+def test_empty_batch_and_max_window():
+    sd = O.random_state_dict(31)
+    m = make_model(sd)
+    y = m(torch.empty(0, 40, 90, device="cuda"), torch.empty(0, 40, 131, device="cuda"))
+    assert tuple(y.shape) == (0, 40, 131)
+    x_imu, x_s = O.synth_inputs(46, 2, 40, nan_frac=1.0)        # every row carries NaN root velocity (DIP data)
+    y = run(m, x_imu, x_s)
+    assert np.isfinite(y).all() and np.abs(y - O.forward(sd, x_imu, x_s)).max() < TOL
+
+
 def test_error_behaviour():
     sd = O.random_state_dict(27)
     m = make_model(sd)

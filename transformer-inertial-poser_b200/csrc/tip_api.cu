@@ -40,6 +40,7 @@ struct tip_model {
     int64_t last_rows = 0;
     int rnn_clusters = -1;          // co-schedulable 8-CTA clusters (queried on first use)
     int rnn_umma_clusters = -1;
+    bool attn_attr_set = false;
     int rnn_stream_fallback = 0;    // TIP_RNN_STREAM=1: L2-streaming kernel (debug / comparison)
     std::string err;
 
@@ -422,13 +423,12 @@ static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, fl
                              int B, int L, float drop_p, uint64_t seed) {
     if (out_lo) {
         // tcgen05 engine: qkv and the output are FP16 hi/lo planes; warp-level tensor-core kernel
-        static bool attr = false;
         static const int hpb = getenv("TIP_ATTN_HPB") ? atoi(getenv("TIP_ATTN_HPB")) : 8;
-        if (!attr) {
+        if (!m->attn_attr_set) {      // function attributes are per device context: once per handle
             cudaFuncSetAttribute(attention_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<8>::SMEM_BYTES);
             cudaFuncSetAttribute(attention_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<4>::SMEM_BYTES);
             cudaFuncSetAttribute(attention_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<2>::SMEM_BYTES);
-            attr = true;
+            m->attn_attr_set = true;
         }
         const __half* qh = reinterpret_cast<const __half*>(qkv);
         const __half* ql = qh + (size_t)m->cap_rows * 3 * E;
