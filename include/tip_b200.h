@@ -132,6 +132,29 @@ int  tip_stream_length(const tip_model* m);   /* current L (0 before the first p
 int  tip_stream_step_raw(tip_model* m, const float* raw_imu, const float* s_row, float* y_last,
                          int rows_on_host, const tip_dropout* drop, void* stream, int* produced);
 
+/* Row N3: closed-loop streaming.  The model-visible part of RTRunnerMin.step AFTER the model
+ * call also runs on the device: the 6-tap 0.6^k output filter and SBP split (real_time_runner_minimal.py:
+ * 87-112), 2-axis -> axis-angle (data_utils.py:164-179), the root rotation taken from the IMU (:161-163),
+ * the averaging with the previous state (:165-167) and record_state_aa_and_c (:78-85, :196), whose row is
+ * fed back as the next x_s row without leaving the GPU.  Per frame the caller pushes one raw IMU row and
+ * reads back the pose.  PyBullet FK and the SBP root-translation correction (:169-194) stay on the CPU:
+ * they only produce s_t[0:3], which the model never sees.
+ *
+ * tip_stream_set_state: the first x_s row of every stream, (S, size_s) fp32 = record_state_aa_and_c(s_init,
+ * zeros) as the runner's constructor appends it (:47); call after tip_stream_reset.
+ * tip_stream_state_width: W = 57 + (size_s - 111) doubles per stream:
+ *   state[0:57] = s_t[3:60] (root axis-angle, 17 joint axis-angles in Nimble order, root velocity),
+ *   state[57:W] = c_t (per SBP: flag in {0,1}, offset xyz in metres).
+ * tip_stream_step_closed: raw_imu (S, 72) fp32 as tip_stream_step_raw; state_out (S, W) float64 (host or
+ * device per rows_on_host).  *produced = 0 during the runner's 5 warm-up calls (state_out untouched).
+ * y_override (optional, same residence as raw_imu): (S, size_s) fp32 used INSTEAD of the model's last
+ * output row by the post step -- teacher forcing, the hook the parity tests use to pin the post step
+ * against a trace of the reference runner independently of the model's own fp32 error. */
+int  tip_stream_set_state(tip_model* m, const float* s_row0, int rows_on_host, void* stream);
+int  tip_stream_state_width(const tip_model* m);
+int  tip_stream_step_closed(tip_model* m, const float* raw_imu, const float* y_override, double* state_out,
+                            int rows_on_host, const tip_dropout* drop, void* stream, int* produced);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 /* Algorithmic bytes / flops of one forward:
  *   bytes = weight_bytes + B*L*4*(d_in + size_s);  flops = 2*MACs. */

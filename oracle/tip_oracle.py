@@ -233,3 +233,154 @@ class WindowAssembler:
             win = np.array(self.acc_sum[-self.max_input_l:]) / ACC_SUM_DOWN_SCALE
             in_imu = np.concatenate((in_imu, win), axis=1)
         return in_imu
+
+
+# ---------------------------------------------------------------------------------------------
+# Post-model step (row N3): restatement of the model-visible part of RTRunnerMin.step after the model
+# call (real_time_runner_minimal.py:87-112 smooth_and_split_s_c, :150-167 state assembly, :78-85/:196
+# record_state_aa_and_c) and of the rotation-representation helpers it uses (data_utils.py:164-187,
+# fairmotion conversions A2R / R2A = scipy Rotation).  PyBullet FK and the SBP root correction
+# (:169-194) only produce the root translation s_t[0:3], which is never fed back to the model, and
+# stay on the CPU (out of scope).  Closed-form numpy, float64 -- except where the reference itself
+# computes in float32 (see PostProcessor.step).
+
+N_DOFS = 57                 # constants.py:24
+DT = 1.0 / 60               # constants.py:7
+
+
+def nearest_rotation(M):
+    """Special-orthogonal estimate of (n,3,3) matrices (orthogonal Procrustes, U V^T) -- what
+    scipy >= 1.11 ``Rotation.from_matrix`` applies to non-orthogonal input (the reference reaches it through
+    fairmotion ``conversions.R2A``, data_utils.py:177; the model's 2-axis output is never exactly
+    orthonormal).  Older scipy skipped this step (version-dependent reference behaviour; goldens were
+    minted with scipy 1.18)."""
+    M = np.asarray(M, dtype=np.float64)
+    U, _, Vt = np.linalg.svd(M)
+    R = U @ Vt
+    neg = np.linalg.det(R) < 0
+    if np.any(neg):
+        U = U.copy()
+        U[neg, :, -1] *= -1
+        R = U @ Vt
+    return R
+
+
+def rotmat_to_quat(R):
+    """(n,3,3) rotation matrices -> (n,4) unit quaternions xyzw (Markley / Shepperd decision method)."""
+    R = np.asarray(R, dtype=np.float64)
+    n = R.shape[0]
+    dec = np.empty((n, 4))
+    dec[:, 0], dec[:, 1], dec[:, 2] = R[:, 0, 0], R[:, 1, 1], R[:, 2, 2]
+    dec[:, 3] = dec[:, :3].sum(axis=1)
+    ch = dec.argmax(axis=1)
+    q = np.empty((n, 4))
+    for idx in range(n):
+        c, Rm = ch[idx], R[idx]
+        if c != 3:
+            i, j, k = c, (c + 1) % 3, (c + 2) % 3
+            q[idx, i] = 1 - dec[idx, 3] + 2 * Rm[i, i]
+            q[idx, j] = Rm[j, i] + Rm[i, j]
+            q[idx, k] = Rm[k, i] + Rm[i, k]
+            q[idx, 3] = Rm[k, j] - Rm[j, k]
+        else:
+            q[idx, 0] = Rm[2, 1] - Rm[1, 2]
+            q[idx, 1] = Rm[0, 2] - Rm[2, 0]
+            q[idx, 2] = Rm[1, 0] - Rm[0, 1]
+            q[idx, 3] = 1 + dec[idx, 3]
+    return q / np.linalg.norm(q, axis=1, keepdims=True)
+
+
+def quat_to_aa(q):
+    """(n,4) xyzw -> (n,3) rotation vectors with angle in [0, pi] (scipy as_rotvec)."""
+    q = np.array(q, dtype=np.float64)
+    q[q[:, 3] < 0] *= -1
+    nrm = np.linalg.norm(q[:, :3], axis=1)
+    angle = 2 * np.arctan2(nrm, q[:, 3])
+    small = angle <= 1e-3
+    scale = np.empty_like(angle)
+    a2 = angle[small] ** 2
+    scale[small] = 2 + a2 / 12 + 7 * a2 * a2 / 2880
+    scale[~small] = angle[~small] / np.sin(angle[~small] / 2)
+    return q[:, :3] * scale[:, None]
+
+
+def rotmat_to_aa(R):
+    """fairmotion conversions.R2A == scipy Rotation.from_matrix(R).as_rotvec()."""
+    return quat_to_aa(rotmat_to_quat(nearest_rotation(R)))
+
+
+def aa_to_rotmat(A):
+    """fairmotion conversions.A2R == scipy Rotation.from_rotvec(A).as_matrix() (Rodrigues via quaternion)."""
+    A = np.asarray(A, dtype=np.float64)
+    angle = np.linalg.norm(A, axis=1)
+    small = angle <= 1e-3
+    scale = np.empty_like(angle)
+    a2 = angle[small] ** 2
+    scale[small] = 0.5 - a2 / 48 + a2 * a2 / 3840
+    scale[~small] = np.sin(angle[~small] / 2) / angle[~small]
+    x, y, z = (A * scale[:, None]).T
+    w = np.cos(angle / 2)
+    R = np.empty((A.shape[0], 3, 3))
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - z * w); R[:, 0, 2] = 2 * (x * z + y * w)
+    R[:, 1, 0] = 2 * (x * y + z * w); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - x * w)
+    R[:, 2, 0] = 2 * (x * z - y * w); R[:, 2, 1] = 2 * (y * z + x * w); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def rot6_to_aa(rm):
+    """data_utils.py:164-179 batch_rot_mat_2axis_to_aa for one frame: (Nj*6,) -> (Nj*3,).  Runs in the dtype
+    of ``rm`` up to the R2A call, like the reference (float32 while the runner passes the raw model row)."""
+    rm = np.asarray(rm).reshape(-1, 3, 2)
+    a1 = rm[:, :, 0] / (np.linalg.norm(rm[:, :, 0], axis=1, keepdims=True) + 1e-6)
+    a2 = rm[:, :, 1] / (np.linalg.norm(rm[:, :, 1], axis=1, keepdims=True) + 1e-6)
+    a3 = np.cross(a1, a2)
+    full = np.stack((a1, a2, a3), axis=2)
+    return rotmat_to_aa(full).reshape(-1)
+
+
+def state_to_row(cur_s, cur_c):
+    """real_time_runner_minimal.py:78-85 + data_utils.py:182-187: (114,) qdq and (20,) constraints ->
+    the (131,) row appended to s_and_c_in_buffer."""
+    aa = np.asarray(cur_s, dtype=np.float64)[3:N_DOFS].reshape(-1, 3)
+    r = aa_to_rotmat(aa)[:, :, :2].reshape(-1)
+    return np.concatenate((r, cur_s[N_DOFS:N_DOFS + 3], cur_c))
+
+
+class PostProcessor:
+    """One stream's post-model state machine.  ``step(y_last, root_R_row)`` consumes the model's last
+    output row (float32, as ``y.squeeze(0)[-1].numpy()`` :150) and the 9 root-rotation entries of the
+    newest window row (:163) and returns (s_t[3:60], c_t, next_row) where next_row is what
+    record_state_aa_and_c appends for the next call."""
+
+    def __init__(self, n_sbps=5):
+        self.n_c = n_sbps * 4
+        self.coeff = 0.6 ** np.arange(6)[::-1]                        # :57
+        self.buf = []
+        self.last_tail = None                                           # last_s[6:60]
+
+    def step(self, y_last, root_R_row):
+        y = np.array(y_last, dtype=np.float32)                          # the buffer keeps THIS array (:91)
+        self.buf.append(y)
+        if len(self.buf) >= 6:                                          # :93-96
+            s = np.array(self.buf[-6:]) * self.coeff[:, None]
+            s_smooth = np.sum(s, axis=0) / np.sum(self.coeff)
+        else:                                                           # :98: a float32 VIEW of the buffer
+            s_smooth = y                                                # entry -- :107-110 edit it in place
+        st = s_smooth[:-self.n_c]
+        c_t = s_smooth[-self.n_c:]
+        c_t[0::4] = (c_t[0::4] > 0.0) * 1.0                            # :107
+        c_t[1::4] /= 5.0
+        c_t[2::4] /= 5.0
+        c_t[3::4] /= 5.0
+        root_v = st[-3:]
+        st_aa = rot6_to_aa(st[:-3])                                     # :155
+        tail = np.zeros(N_DOFS - 6 + 3)                                 # s_t[6:60]
+        tail[:N_DOFS - 6] = st_aa[3:]                                   # :160
+        tail[N_DOFS - 6:] = root_v                                      # :158
+        root_aa = rotmat_to_aa(np.asarray(root_R_row, dtype=np.float64).reshape(1, 3, 3))[0]   # :161-162
+        if self.last_tail is not None:                                  # :165-166 (s_t[60:] stays 0)
+            tail = (tail + self.last_tail) / 2.0
+        self.last_tail = tail.copy()
+        s = np.concatenate((root_aa, tail))                             # s_t[3:60]
+        row = np.concatenate((aa_to_rotmat(s[:54].reshape(-1, 3))[:, :, :2].reshape(-1), s[54:57], c_t))
+        return s, np.array(c_t, dtype=np.float64), row

@@ -48,7 +48,7 @@ def _weights(g):
 
 
 FIXTURES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLD, "*.npz"))
-                  if "stream" not in p and "b256" not in p)
+                  if "stream" not in p and "b256" not in p and "runner" not in p)
 ENGINES = [pytest.param(1, id="ffma"), pytest.param(2, id="tcgen05")]   # tip_set_gemm_engine
 
 

@@ -23,7 +23,7 @@ def _weights(g):
 
 
 FIXTURES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLD, "*.npz"))
-                  if "stream" not in p and "b256" not in p)
+                  if "stream" not in p and "b256" not in p and "runner" not in p)
 
 
 def test_fixture_inventory():

@@ -67,6 +67,11 @@ struct tip_model {
     float *raw_ring = nullptr, *st_raw = nullptr, *h_raw = nullptr;    // N1: raw-IMU pre-processing state
     double* acc_ring = nullptr;
     int n_raw = 0, n_rows = 0;
+    // N3: post-model step state (closed loop)
+    float* fb_s = nullptr;                 // (S, size_s) row fed back as the next x_s row
+    double *pp_ring = nullptr, *pp_last = nullptr, *pp_out = nullptr, *h_pp_out = nullptr;
+    int n_post = 0;
+    bool fb_set = false;
     cudaGraphExec_t st_graph = nullptr;   // captured steady-state step (L == MAXL)
     int st_graph_launches = 0;
 
@@ -178,7 +183,12 @@ static void free_stream_state(tip_model* m) {
     if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
     if (m->acc_ring) { cudaFree(m->acc_ring); m->acc_ring = nullptr; }
     if (m->h_raw) { cudaFreeHost(m->h_raw); m->h_raw = nullptr; }
-    m->n_raw = m->n_rows = 0;
+    if (m->fb_s) { cudaFree(m->fb_s); m->fb_s = nullptr; }
+    for (double** p : {&m->pp_ring, &m->pp_last, &m->pp_out})
+        if (*p) { cudaFree(*p); *p = nullptr; }
+    if (m->h_pp_out) { cudaFreeHost(m->h_pp_out); m->h_pp_out = nullptr; }
+    m->n_raw = m->n_rows = m->n_post = 0;
+    m->fb_set = false;
     for (float** p : {&m->win_imu, &m->win_s, &m->st_rows, &m->st_ximu, &m->st_xs, &m->st_y, &m->st_ylast, &m->raw_ring, &m->st_raw})
         if (*p) { cudaFree(*p); *p = nullptr; }
     for (float** p : {&m->h_rows, &m->h_ylast})
@@ -460,9 +470,10 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
         q.attrs = nullptr; q.numAttrs = 0;   // the kernel carries __cluster_dims__ itself
         (void)at;
         int n = 0;
+        const cudaError_t pending = cudaPeekAtLastError();     // an earlier launch error must survive the query
         cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, rnn_cluster_kernel, &q);
         if (getenv("TIP_VERBOSE")) fprintf(stderr, "[tip] cudaOccupancyMaxActiveClusters -> %d (%s)\n", n, cudaGetErrorString(qe));
-        if (qe != cudaSuccess || n < 1) { n = 0; cudaGetLastError(); }
+        if (qe != cudaSuccess || n < 1) { n = 0; if (pending == cudaSuccess) cudaGetLastError(); }
         if (getenv("TIP_RNN_CLUSTERS")) n = atoi(getenv("TIP_RNN_CLUSTERS"));
         if (getenv("TIP_VERBOSE")) fprintf(stderr, "[tip] rnn clusters co-schedulable: %d\n", n);
         m->rnn_clusters = n;
@@ -475,7 +486,8 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
             cudaLaunchConfig_t q{};
             q.gridDim = dim3(RU_CTAS * 18); q.blockDim = dim3(RU_THREADS); q.dynamicSmemBytes = RU_SMEM_BYTES;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, rnn_umma_kernel, &q) != cudaSuccess || n < 1) { n = 0; cudaGetLastError(); }
+            const cudaError_t pending = cudaPeekAtLastError();
+            if (cudaOccupancyMaxActiveClusters(&n, rnn_umma_kernel, &q) != cudaSuccess || n < 1) { n = 0; if (pending == cudaSuccess) cudaGetLastError(); }
             if (getenv("TIP_VERBOSE")) fprintf(stderr, "[tip] rnn_umma clusters co-schedulable: %d\n", n);
             m->rnn_umma_clusters = n;
         }
@@ -787,6 +799,13 @@ extern "C" int tip_stream_reset(tip_model* m, int n_streams) {
     TIP_CUDA_TRY(m, cudaMalloc(&m->st_raw, S * IMU_RAW * sizeof(float)));
     TIP_CUDA_TRY(m, cudaMalloc(&m->acc_ring, S * ACC_WIN * 18 * sizeof(double)));
     TIP_CUDA_TRY(m, cudaMallocHost(&m->h_raw, S * IMU_RAW * sizeof(float)));
+    const size_t out_w = 57 + (d.size_s - 111);
+    TIP_CUDA_TRY(m, cudaMalloc(&m->fb_s, S * d.size_s * sizeof(float)));
+    TIP_CUDA_TRY(m, cudaMalloc(&m->pp_ring, S * PP_TAPS * d.size_s * sizeof(double)));
+    TIP_CUDA_TRY(m, cudaMalloc(&m->pp_last, S * PP_TAIL * sizeof(double)));
+    TIP_CUDA_TRY(m, cudaMalloc(&m->pp_out, S * out_w * sizeof(double)));
+    TIP_CUDA_TRY(m, cudaMallocHost(&m->h_pp_out, S * out_w * sizeof(double)));
+    TIP_CUDA_TRY(m, cudaMemset(m->fb_s, 0, S * d.size_s * sizeof(float)));
     TIP_CUDA_TRY(m, cudaMemset(m->win_imu, 0, S * MAXL * d.n_imu * sizeof(float)));
     TIP_CUDA_TRY(m, cudaMemset(m->win_s, 0, S * MAXL * d.size_s * sizeof(float)));
     m->n_streams = n_streams;
@@ -865,6 +884,7 @@ static int stream_step_core(tip_model* m, float* y_last, int rows_on_host, const
         if (rc != TIP_OK) return rc;
     }
     m->stream_len = std::min(len_before + 1, MAXL);
+    if (!y_last) return TIP_OK;               // closed loop: the caller consumes st_ylast on the device
     if (rows_on_host) {
         TIP_CUDA_TRY(m, cudaMemcpyAsync(m->h_ylast, m->st_ylast, n_s * sizeof(float), cudaMemcpyDeviceToHost, st));
         TIP_CUDA_TRY(m, cudaStreamSynchronize(st));
@@ -928,4 +948,80 @@ extern "C" int tip_stream_step_raw(tip_model* m, const float* raw_imu, const flo
     m->n_rows += 1;
     *produced = 1;
     return stream_step_core(m, y_last, rows_on_host, drop, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row N3: closed loop -- post-model step on the device, state row fed back without leaving the GPU.
+extern "C" int tip_stream_state_width(const tip_model* m) { return m ? 57 + (m->d.size_s - 111) : 0; }
+
+extern "C" int tip_stream_set_state(tip_model* m, const float* s_row0, int rows_on_host, void* stream_) {
+    if (!m || !s_row0) return TIP_ERR_INVALID_ARG;
+    if (m->n_streams < 1) { m->set_error("tip_stream_set_state before tip_stream_reset"); return TIP_ERR_INVALID_ARG; }
+    cudaStream_t st = (cudaStream_t)stream_;
+    TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    const size_t bytes = (size_t)m->n_streams * m->d.size_s * sizeof(float);
+    if (rows_on_host) {
+        memcpy(m->h_rows, s_row0, bytes);
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->fb_s, m->h_rows, bytes, cudaMemcpyHostToDevice, st));
+        TIP_CUDA_TRY(m, cudaStreamSynchronize(st));
+    } else {
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->fb_s, s_row0, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    m->fb_set = true;
+    return TIP_OK;
+}
+
+extern "C" int tip_stream_step_closed(tip_model* m, const float* raw_imu, const float* y_override, double* state_out,
+                                      int rows_on_host, const tip_dropout* drop, void* stream_, int* produced) {
+    if (!m || !raw_imu || !state_out || !produced) return TIP_ERR_INVALID_ARG;
+    if (!m->packed) { m->set_error("tip_stream_step_closed before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
+    if (m->n_streams < 1 || !m->fb_set) {
+        m->set_error("tip_stream_step_closed needs tip_stream_reset and tip_stream_set_state first");
+        return TIP_ERR_INVALID_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream_;
+    TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    const Dims& d = m->d;
+    const size_t S = m->n_streams;
+    const size_t n_i = S * d.n_imu, n_s = S * d.size_s, n_r = S * IMU_RAW;
+    const size_t out_w = 57 + (d.size_s - 111);
+    if (rows_on_host) {
+        memcpy(m->h_raw, raw_imu, n_r * sizeof(float));
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_raw, m->h_raw, n_r * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_raw, raw_imu, n_r * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    // the x_s row of this call is the one the previous post step produced (or the initial state)
+    TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows + n_i, m->fb_s, n_s * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    imu_push_kernel<<<(unsigned)S, 32, 0, st>>>(m->st_raw, m->raw_ring, m->acc_ring, m->st_rows, d.n_imu, m->n_raw, m->n_rows);
+    TIP_CUDA_TRY(m, cudaGetLastError());
+    m->n_raw += (m->n_raw == 0) ? IMU_DELAY + 1 : 1;
+    if (m->n_raw < IMU_RING) {
+        *produced = 0;
+        if (rows_on_host) TIP_CUDA_TRY(m, cudaStreamSynchronize(st));
+        return TIP_OK;
+    }
+    m->n_rows += 1;
+    *produced = 1;
+    int rc = stream_step_core(m, nullptr, rows_on_host, drop, st);
+    if (rc != TIP_OK) return rc;
+    const float* ysrc = m->st_ylast;
+    if (y_override) {                       // teacher forcing (parity tests): st_y is free after the last-row gather
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_y, y_override, n_s * sizeof(float),
+                                        rows_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+        ysrc = m->st_y;
+    }
+    post_step_kernel<<<(unsigned)S, 32, 0, st>>>(ysrc, m->st_rows, d.n_imu, m->pp_ring, m->pp_last, m->fb_s, m->pp_out,
+                                                 d.size_s, m->n_post);
+    TIP_CUDA_TRY(m, cudaGetLastError());
+    m->launches += 2;                       // imu_push + post_step
+    m->n_post += 1;
+    if (rows_on_host) {
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->h_pp_out, m->pp_out, S * out_w * sizeof(double), cudaMemcpyDeviceToHost, st));
+        TIP_CUDA_TRY(m, cudaStreamSynchronize(st));
+        memcpy(state_out, m->h_pp_out, S * out_w * sizeof(double));
+    } else {
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(state_out, m->pp_out, S * out_w * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    return TIP_OK;
 }

@@ -763,6 +763,181 @@ imu_push_kernel(const float* __restrict__ raw_new, float* __restrict__ raw_ring,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row N3: the model-visible part of RTRunnerMin.step AFTER the model call, on the device
+// (real_time_runner_minimal.py:87-112 smooth_and_split_s_c, :150-167 state assembly, :78-85/:196
+// record_state_aa_and_c; data_utils.py:164-187; fairmotion A2R / R2A = scipy Rotation).  One warp per
+// stream, double arithmetic like the reference's float64 buffers -- except during the first five model
+// calls, where the reference works on the raw float32 output row itself (:98 returns it un-copied, so
+// the normalisation / cross product of data_utils.py:170-172 run in float32 and :107-110 edit the
+// buffered row in place); both quirks are kept.  PyBullet FK and the SBP root correction (:169-194)
+// only produce the root translation, which is never fed back, and stay on the CPU.
+//   out_state[s] = [ s_t[3:60] (root aa from the IMU, 17 joint aa, root velocity) | c_t ]   (57 + n_c doubles)
+//   fb_row[s]    = the (size_s,) float row record_state_aa_and_c appends for the next call.
+constexpr int PP_TAPS = 6, PP_NJ = 18, PP_TAIL = 54;
+
+// nearest rotation (orthogonal Procrustes, what scipy's Rotation.from_matrix applies to non-orthogonal
+// input): Newton iteration X <- (X + X^-T) / 2 on the polar factor, then Markley's matrix->quaternion
+// and the rotation-vector log map of scipy's as_rotvec.
+__device__ inline void pp_rotmat_to_aa(const double* M, double* aa) {
+    double X[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) X[i] = M[i];
+    for (int it = 0; it < 60; ++it) {
+        double C[9];
+        C[0] = X[4] * X[8] - X[5] * X[7]; C[1] = X[5] * X[6] - X[3] * X[8]; C[2] = X[3] * X[7] - X[4] * X[6];
+        C[3] = X[2] * X[7] - X[1] * X[8]; C[4] = X[0] * X[8] - X[2] * X[6]; C[5] = X[1] * X[6] - X[0] * X[7];
+        C[6] = X[1] * X[5] - X[2] * X[4]; C[7] = X[2] * X[3] - X[0] * X[5]; C[8] = X[0] * X[4] - X[1] * X[3];
+        const double det = X[0] * C[0] + X[1] * C[1] + X[2] * C[2];
+        if (!(fabs(det) > 1e-300)) break;
+        double delta = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const double nx = 0.5 * (X[i] + C[i] / det);     // cofactor / det = X^-T
+            delta = fmax(delta, fabs(nx - X[i]));
+            X[i] = nx;
+        }
+        if (delta < 1e-15) break;
+    }
+    const double d0 = X[0], d1 = X[4], d2 = X[8], tr = d0 + d1 + d2;
+    double q[4];
+    int c = 0;
+    double best = d0;
+    if (d1 > best) { best = d1; c = 1; }
+    if (d2 > best) { best = d2; c = 2; }
+    if (tr > best) c = 3;
+    if (c != 3) {
+        const int i = c, j = (c + 1) % 3, k = (c + 2) % 3;
+        q[i] = 1.0 - tr + 2.0 * X[i * 3 + i];
+        q[j] = X[j * 3 + i] + X[i * 3 + j];
+        q[k] = X[k * 3 + i] + X[i * 3 + k];
+        q[3] = X[k * 3 + j] - X[j * 3 + k];
+    } else {
+        q[0] = X[7] - X[5]; q[1] = X[2] - X[6]; q[2] = X[3] - X[1]; q[3] = 1.0 + tr;
+    }
+    const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    double sgn = (q[3] < 0.0) ? -1.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = sgn * q[i] / qn;
+    const double vn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    const double angle = 2.0 * atan2(vn, q[3]);
+    double scale;
+    if (angle <= 1e-3) { const double a2 = angle * angle; scale = 2.0 + a2 / 12.0 + 7.0 * a2 * a2 / 2880.0; }
+    else scale = angle / sin(angle / 2.0);
+    aa[0] = q[0] * scale; aa[1] = q[1] * scale; aa[2] = q[2] * scale;
+}
+
+// first two columns of the rotation matrix of a rotation vector (scipy from_rotvec().as_matrix())
+__device__ inline void pp_aa_to_rot6(const double* a, double* r6) {
+    const double angle = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    double scale;
+    if (angle <= 1e-3) { const double a2 = angle * angle; scale = 0.5 - a2 / 48.0 + a2 * a2 / 3840.0; }
+    else scale = sin(angle / 2.0) / angle;
+    const double x = a[0] * scale, y = a[1] * scale, z = a[2] * scale, w = cos(angle / 2.0);
+    r6[0] = 1.0 - 2.0 * (y * y + z * z); r6[1] = 2.0 * (x * y - z * w);
+    r6[2] = 2.0 * (x * y + z * w);       r6[3] = 1.0 - 2.0 * (x * x + z * z);
+    r6[4] = 2.0 * (x * z - y * w);       r6[5] = 2.0 * (y * z + x * w);
+}
+
+__global__ void __launch_bounds__(32)
+post_step_kernel(const float* __restrict__ y_last, const float* __restrict__ imu_rows, int n_imu,
+                 double* __restrict__ ring, double* __restrict__ last_tail, float* __restrict__ fb_row,
+                 double* __restrict__ out_state, int size_s, int n_before) {
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const int n_c = size_s - 111, out_w = 57 + n_c;
+    double* rg = ring + (size_t)s * PP_TAPS * size_s;
+    double* lt = last_tail + (size_t)s * PP_TAIL;
+    const float* y = y_last + (size_t)s * size_s;
+    double* out = out_state + (size_t)s * out_w;
+    float* fb = fb_row + (size_t)s * size_s;
+    __shared__ double sm[160];          // smoothed row
+    __shared__ double st[57];           // s_t[3:60]
+    const bool mode32 = (n_before + 1) < PP_TAPS;
+    const int slot = n_before % PP_TAPS;
+    for (int c = lane; c < size_s; c += 32) rg[slot * size_s + c] = (double)y[c];
+    __syncwarp();
+    if (!mode32) {
+        // np.sum(buf[-6:] * coeff[:, None], axis=0) / np.sum(coeff), coeff = 0.6 ** [5..0]      (:93-96)
+        const double cf[PP_TAPS] = {0.07776, 0.1296, 0.216, 0.36, 0.6, 1.0};
+        double csum = 0.0;
+#pragma unroll
+        for (int k = 0; k < PP_TAPS; ++k) csum += pow(0.6, (double)(PP_TAPS - 1 - k));
+        for (int c = lane; c < size_s; c += 32) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < PP_TAPS; ++k)
+                acc += rg[((n_before + 1 - PP_TAPS + k) % PP_TAPS) * size_s + c] * pow(0.6, (double)(PP_TAPS - 1 - k));
+            (void)cf;
+            sm[c] = acc / csum;
+        }
+    } else {
+        for (int c = lane; c < size_s; c += 32) sm[c] = (double)y[c];
+    }
+    __syncwarp();
+    // SBP block: flag = logit > 0, offsets / 5                                                    (:103-110)
+    for (int c = 111 + lane; c < size_s; c += 32) {
+        const int k = (c - 111) & 3;
+        double v = sm[c];
+        if (k == 0) v = v > 0.0 ? 1.0 : 0.0;
+        else v = mode32 ? (double)__fdiv_rn((float)v, 5.0f) : v / 5.0;
+        sm[c] = v;
+        if (mode32) rg[slot * size_s + c] = v;            // the reference edits the buffered row in place
+    }
+    __syncwarp();
+    // 2-axis -> rotation vector per joint                                        (data_utils.py:164-179)
+    if (lane < PP_NJ) {
+        double M[9];
+        const double* v = sm + 6 * lane;                  // (3, 2) row-major: columns a1 = v[0,2,4], a2 = v[1,3,5]
+        if (mode32) {
+            const float x0 = (float)v[0], x1 = (float)v[2], x2 = (float)v[4];
+            const float y0 = (float)v[1], y1 = (float)v[3], y2 = (float)v[5];
+            const float n1 = __fadd_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2))), 1e-6f);
+            const float n2 = __fadd_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(y0, y0), __fmul_rn(y1, y1)), __fmul_rn(y2, y2))), 1e-6f);
+            const float a0 = __fdiv_rn(x0, n1), a1 = __fdiv_rn(x1, n1), a2 = __fdiv_rn(x2, n1);
+            const float b0 = __fdiv_rn(y0, n2), b1 = __fdiv_rn(y1, n2), b2 = __fdiv_rn(y2, n2);
+            const float c0 = __fsub_rn(__fmul_rn(a1, b2), __fmul_rn(a2, b1));
+            const float c1 = __fsub_rn(__fmul_rn(a2, b0), __fmul_rn(a0, b2));
+            const float c2 = __fsub_rn(__fmul_rn(a0, b1), __fmul_rn(a1, b0));
+            M[0] = a0; M[1] = b0; M[2] = c0; M[3] = a1; M[4] = b1; M[5] = c1; M[6] = a2; M[7] = b2; M[8] = c2;
+        } else {
+            const double n1 = sqrt(v[0] * v[0] + v[2] * v[2] + v[4] * v[4]) + 1e-6;
+            const double n2 = sqrt(v[1] * v[1] + v[3] * v[3] + v[5] * v[5]) + 1e-6;
+            const double a0 = v[0] / n1, a1 = v[2] / n1, a2 = v[4] / n1;
+            const double b0 = v[1] / n2, b1 = v[3] / n2, b2 = v[5] / n2;
+            M[0] = a0; M[1] = b0; M[2] = a1 * b2 - a2 * b1;
+            M[3] = a1; M[4] = b1; M[5] = a2 * b0 - a0 * b2;
+            M[6] = a2; M[7] = b2; M[8] = a0 * b1 - a1 * b0;
+        }
+        double aa[3];
+        if (lane == 0) {                                  // root: taken from the IMU, not the prediction (:161-163)
+            const float* rr = imu_rows + (size_t)s * n_imu;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) M[i] = (double)rr[i];
+        }
+        pp_rotmat_to_aa(M, aa);
+        st[3 * lane] = aa[0]; st[3 * lane + 1] = aa[1]; st[3 * lane + 2] = aa[2];
+    }
+    if (lane >= 29) st[54 + lane - 29] = sm[108 + lane - 29];          // root velocity (:157-158)
+    __syncwarp();
+    // "To make motion a bit smoother": average s_t[6:] with the previous frame's                  (:165-167)
+    for (int c = lane; c < PP_TAIL; c += 32) {
+        double v = st[3 + c];
+        if (n_before > 0) v = (v + lt[c]) / 2.0;
+        lt[c] = v;
+        st[3 + c] = v;
+    }
+    __syncwarp();
+    for (int c = lane; c < 57; c += 32) out[c] = st[c];
+    for (int c = lane; c < n_c; c += 32) { out[57 + c] = sm[111 + c]; fb[111 + c] = (float)sm[111 + c]; }
+    if (lane < PP_NJ) {                                   // record_state_aa_and_c                   (:78-85)
+        double r6[6];
+        pp_aa_to_rot6(st + 3 * lane, r6);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) fb[6 * lane + i] = (float)r6[i];
+    }
+    if (lane >= 29) fb[108 + lane - 29] = (float)st[54 + lane - 29];
+}
+
 // gather compacted (S, L, width) windows out of the (S, MAXL, width) storage when L < MAXL
 __global__ void window_compact_kernel(const float* __restrict__ win, float* __restrict__ out,
                                       int S, int L, int width) {

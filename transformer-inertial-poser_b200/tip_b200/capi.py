@@ -51,6 +51,10 @@ SIGNATURES = {
     "tip_stream_length": (C.c_int, [_VP]),
     "tip_stream_step_raw": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.POINTER(TipDropout), _VP,
                                       C.POINTER(C.c_int)]),
+    "tip_stream_set_state": (C.c_int, [_VP, _VP, C.c_int, _VP]),
+    "tip_stream_state_width": (C.c_int, [_VP]),
+    "tip_stream_step_closed": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.POINTER(TipDropout), _VP,
+                                         C.POINTER(C.c_int)]),
     "tip_algorithmic_cost": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double)]),
     "tip_last_launch_count": (C.c_int, [_VP]),
