@@ -27,6 +27,27 @@ struct PipeCtx {
     cudaEvent_t ev_in[8], ev_out[8];
 };
 
+// CUDA graphs of whole forwards, keyed by everything a captured launch sequence depends on.  A (shape,
+// pointer) combination is captured the second time it is seen (the first call runs eagerly and does all the
+// lazy initialisation: workspace, tensor maps, occupancy queries), then replayed: one graph launch instead
+// of ~25 kernel launches.
+struct FwdGraphKey {
+    const void *x_imu, *x_s, *y, *keep;
+    int B, L, engine;
+    float past_scale;
+    bool operator==(const FwdGraphKey& o) const {
+        return x_imu == o.x_imu && x_s == o.x_s && y == o.y && keep == o.keep && B == o.B && L == o.L &&
+               engine == o.engine && past_scale == o.past_scale;
+    }
+};
+struct FwdGraph {
+    FwdGraphKey key{};
+    cudaGraphExec_t exec = nullptr;     // null: seen once, not captured yet
+    int launches = 0;
+    uint64_t last_use = 0;
+};
+constexpr int FWD_GRAPH_SLOTS = 8;
+
 struct tip_model {
     tip_dims cdims{};
     Dims d{};
@@ -74,6 +95,8 @@ struct tip_model {
     bool fb_set = false;
     cudaGraphExec_t st_graph = nullptr;   // captured steady-state step (L == MAXL)
     int st_graph_launches = 0;
+    FwdGraph fwd_graphs[FWD_GRAPH_SLOTS];
+    uint64_t fwd_tick = 0;
 
     // per-stage profiling (tip_set_profile)
     int profile = 0;
@@ -98,6 +121,15 @@ static void mark(tip_model* m, cudaStream_t st, const char* name, int layer = -1
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// every captured graph bakes in workspace addresses, tensor maps and the engine choice
+static void drop_graphs(tip_model* m) {
+    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    for (FwdGraph& g : m->fwd_graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g = FwdGraph{};
+    }
+}
 
 static void compute_offsets(tip_model* m) {
     const Dims& d = m->d;
@@ -180,7 +212,7 @@ extern "C" int tip_create(const tip_dims* dims, tip_model** out) {
 }
 
 static void free_stream_state(tip_model* m) {
-    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    drop_graphs(m);
     if (m->acc_ring) { cudaFree(m->acc_ring); m->acc_ring = nullptr; }
     if (m->h_raw) { cudaFreeHost(m->h_raw); m->h_raw = nullptr; }
     if (m->fb_s) { cudaFree(m->fb_s); m->fb_s = nullptr; }
@@ -294,7 +326,7 @@ extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64
     TIP_CUDA_TRY(m, cudaGetLastError());
     m->packed = true;
     m->maps_ready = false;
-    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    drop_graphs(m);
     return TIP_OK;
 }
 
@@ -313,13 +345,13 @@ extern "C" int tip_mark_packed(tip_model* m) {
 extern "C" int tip_set_gemm_engine(tip_model* m, int engine) {
     if (!m || engine < 0 || engine > 2) return TIP_ERR_INVALID_ARG;
     m->engine = engine;
-    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    drop_graphs(m);
     return TIP_OK;
 }
 extern "C" int tip_set_use_graphs(tip_model* m, int enable) {
     if (!m) return TIP_ERR_INVALID_ARG;
     m->use_graphs = enable ? 1 : 0;
-    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    drop_graphs(m);
     return TIP_OK;
 }
 extern "C" int tip_last_launch_count(const tip_model* m) { return m ? m->launches : 0; }
@@ -337,7 +369,7 @@ extern "C" int tip_set_profile(tip_model* m, int enable) {
     m->profile = enable ? 1 : 0;
     m->st_names.clear();
     m->st_layers.clear();
-    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    drop_graphs(m);
     return TIP_OK;
 }
 extern "C" int tip_profile_stages(const tip_model* m) { return m ? (int)m->st_names.size() : 0; }
@@ -413,7 +445,7 @@ static int ensure_workspace(tip_model* m, int rows) {
     m->att = m->ws + o_att; m->hid = m->ws + o_hid; m->gi = m->ws + o_gi; m->hs = m->ws + o_hs;
     m->cap_rows = cap;
     m->maps_ready = false;
-    if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
+    drop_graphs(m);
     return TIP_OK;
 }
 
@@ -482,21 +514,30 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
     if (hs_lo && m->maps_ready && rnn_kind != 1 && !m->rnn_stream_fallback) {
         // tensor-core recurrence (tcgen05 engine): clusters of 8 CTAs, RU_N windows each
         if (m->rnn_umma_clusters < 0) {
-            cudaFuncSetAttribute(rnn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM_BYTES);
+            cudaFuncSetAttribute(rnn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM_BYTES);
+            cudaFuncSetAttribute(rnn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM_BYTES);
             cudaLaunchConfig_t q{};
             q.gridDim = dim3(RU_CTAS * 18); q.blockDim = dim3(RU_THREADS); q.dynamicSmemBytes = RU_SMEM_BYTES;
             int n = 0;
             const cudaError_t pending = cudaPeekAtLastError();
-            if (cudaOccupancyMaxActiveClusters(&n, rnn_umma_kernel, &q) != cudaSuccess || n < 1) { n = 0; if (pending == cudaSuccess) cudaGetLastError(); }
+            if (cudaOccupancyMaxActiveClusters(&n, rnn_umma_kernel<false>, &q) != cudaSuccess || n < 1) { n = 0; if (pending == cudaSuccess) cudaGetLastError(); }
             if (getenv("TIP_VERBOSE")) fprintf(stderr, "[tip] rnn_umma clusters co-schedulable: %d\n", n);
             m->rnn_umma_clusters = n;
         }
         if (m->rnn_umma_clusters > 0) {
             const int blocks = (B + RU_N - 1) / RU_N;
             const int nc = std::min(blocks, m->rnn_umma_clusters);
-            rnn_umma_kernel<<<nc * RU_CTAS, RU_THREADS, RU_SMEM_BYTES, st>>>(
-                m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
-                m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf);
+            static const int a_tmem = getenv("TIP_RNN_TMEMA") ? atoi(getenv("TIP_RNN_TMEMA")) : 0;
+            const __half* wh = reinterpret_cast<const __half*>(m->blob + m->off.whh_hi);
+            const __half* wl = reinterpret_cast<const __half*>(m->blob + m->off.whh_lo);
+            if (a_tmem)
+                rnn_umma_kernel<true><<<nc * RU_CTAS, RU_THREADS, RU_SMEM_BYTES, st>>>(
+                    m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
+                    m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf, wh, wl);
+            else
+                rnn_umma_kernel<false><<<nc * RU_CTAS, RU_THREADS, RU_SMEM_BYTES, st>>>(
+                    m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
+                    m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf, wh, wl);
             m->launches++;
             return;
         }
@@ -661,6 +702,54 @@ extern "C" int tip_forward(tip_model* m, const float* x_imu, const float* x_s, f
     TIP_CUDA_TRY(m, cudaSetDevice(m->device));
     m->launches = 0;
     const Dims& d = m->d;
+    const bool stochastic = drop && (drop->in_dropout > 0.f || drop->past_state_dropout > 0.f || drop->encoder_dropout > 0.f);
+    FwdGraph* slot = nullptr;
+    if (m->use_graphs && !m->profile && !stochastic && B <= CHUNK_WINDOWS && !getenv("TIP_NO_FWD_GRAPH")) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+            const FwdGraphKey key{x_imu, x_s, y, keep_mask, B, L, m->engine, past_scale};
+            FwdGraph* lru = &m->fwd_graphs[0];
+            for (FwdGraph& g : m->fwd_graphs) {
+                if (g.last_use && g.key == key) { slot = &g; break; }
+                if (g.last_use < lru->last_use) lru = &g;
+            }
+            if (slot && slot->exec) {                                    // replay
+                slot->last_use = ++m->fwd_tick;
+                TIP_CUDA_TRY(m, cudaGraphLaunch(slot->exec, st));
+                m->launches = slot->launches;
+                m->last_rows = (int64_t)B * L;
+                return TIP_OK;
+            }
+            if (!slot) {                                                 // first sighting: run eagerly, remember the key
+                if (lru->exec) cudaGraphExecDestroy(lru->exec);
+                *lru = FwdGraph{};
+                lru->key = key;
+                lru->last_use = ++m->fwd_tick;
+            }
+        }
+    }
+    if (slot) {
+        // second sighting: capture this forward (all lazy initialisation happened on the first, eager call)
+        cudaStream_t cstream;
+        TIP_CUDA_TRY(m, cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking));
+        cudaGraph_t g = nullptr;
+        TIP_CUDA_TRY(m, cudaStreamBeginCapture(cstream, cudaStreamCaptureModeThreadLocal));
+        int rc = forward_chunk(m, x_imu, x_s, y, B, L, keep_mask, past_scale, drop, cstream);
+        cudaError_t ce = cudaStreamEndCapture(cstream, &g);
+        cudaGraphExec_t exec = nullptr;
+        if (rc == TIP_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, g, 0);
+        if (g) cudaGraphDestroy(g);
+        cudaStreamDestroy(cstream);
+        if (rc != TIP_OK) return rc;
+        if (ce != cudaSuccess) { m->set_error(std::string("forward graph capture: ") + cudaGetErrorString(ce)); return TIP_ERR_CUDA; }
+        // forward_chunk may have re-allocated the workspace (drop_graphs) -- then `slot` was reset; re-take it
+        slot->key = FwdGraphKey{x_imu, x_s, y, keep_mask, B, L, m->engine, past_scale};
+        slot->exec = exec;
+        slot->launches = m->launches;
+        slot->last_use = ++m->fwd_tick;
+        TIP_CUDA_TRY(m, cudaGraphLaunch(exec, st));
+        return TIP_OK;
+    }
     for (int b0 = 0; b0 < B; b0 += CHUNK_WINDOWS) {
         const int nb = std::min(CHUNK_WINDOWS, B - b0);
         const size_t r0 = (size_t)b0 * L;

@@ -36,11 +36,18 @@ constexpr int RU_B_BYTES = 8 * RU_B_KB_BYTES;         // 48 KB per parity
 constexpr int RU_SMEM_BYTES = RU_A_BYTES + 2 * RU_B_BYTES + 256;
 constexpr uint32_t RU_PUSH_BYTES = (RU_CTAS - 1) * RU_B_KB_BYTES;         // what the 7 peers deliver per step
 constexpr int RU_TMEM_COLS = 64;
+// A_TMEM variant: the W_hh slice lives in TENSOR MEMORY instead of shared memory (128 lanes x 256 32-bit
+// columns = 128 stacked rows x 512 fp16 k), so each MMA reads only the small h operand from shared memory;
+// the shared-memory read of the 4 KB A slice per MMA is what bounds the issue rate of the SS form.
+constexpr int RU_TMEM_COLS_A = 512;
+constexpr int RU_A_COL0 = 64;                        // first TMEM column of the A operand (D uses [0, 48))
 
+template <bool A_TMEM>
 __global__ void __cluster_dims__(RU_CTAS, 1, 1) __launch_bounds__(RU_THREADS, 1)
 rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
                 const float* __restrict__ gi, __half* __restrict__ hs_hi, __half* __restrict__ hs_lo,
-                const float* __restrict__ acc_scale, int B, int L, unsigned long long* tbuf) {
+                const float* __restrict__ acc_scale, int B, int L, unsigned long long* tbuf,
+                const __half* __restrict__ whh_hi, const __half* __restrict__ whh_lo) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* sA = smem;                                    // [8 kb][128 stacked rows x 128 B]
@@ -64,12 +71,44 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
         ptx::mbar_init(acc_full, 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 0) ptx::tmem_alloc(tmem_slot, RU_TMEM_COLS);
+    if (warp == 0) ptx::tmem_alloc(tmem_slot, A_TMEM ? RU_TMEM_COLS_A : RU_TMEM_COLS);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (threadIdx.x == 0) {
+    if constexpr (A_TMEM) {
+        // resident A operand in tensor memory: TMEM lane 32q + l holds stacked row (q, l) = [hi rows of units
+        // 16q..16q+15 | lo rows of the same units]; 32-bit column c holds k = 2c, 2c+1 (K-major, packed pairs)
+        if (warp >= 1) {
+            const int q = warp & 3, ch = (warp - 1) >> 2;
+            const int unit = (int)rank * RU_UNITS + q * 16 + (lane & 15);
+            const __half* src = ((lane >> 4) ? whh_lo : whh_hi) + (size_t)unit * R + ch * 256;
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                uint32_t r[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i * 64) + j);
+                    r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+                }
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(RU_A_COL0 + ch * 128 + i * 32);
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                    "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                    "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                    ::"r"(ta), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                      "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                      "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+                    : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        ptx::tc_fence_before();
+        __syncthreads();
+        ptx::tc_fence_after();
+    }
+    if (!A_TMEM && threadIdx.x == 0) {
         // resident A operand.  Stacked row order of a k-block: for q = 0..3: 16 hi rows then 16 lo rows of
         // units 16q..16q+15, so both partial rows of a unit sit in the same TMEM lane quarter.
         ptx::mbar_expect_tx(w_full, RU_A_BYTES);
@@ -92,7 +131,7 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
             // ================= MMA issuer =================
             if (lane == 0) {
                 constexpr uint32_t idesc = umma_idesc_f16(2 * RU_UNITS, 2 * RU_N);
-                ptx::mbar_wait(w_full, 0);                 // completes once; later waits return immediately
+                if constexpr (!A_TMEM) ptx::mbar_wait(w_full, 0);   // completes once; later waits return immediately
                 const uint32_t a0 = ptx::smem_u32(sA);
                 for (int t = 1; t < L; ++t) {              // step 0 has h = 0: no product
                     const int cur = t & 1;
@@ -108,7 +147,17 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                            ptx::umma_f16(tmem_base, ad + adv, bd + adv, idesc, (kb | k) ? 1u : 0u);
+                            if constexpr (A_TMEM) {
+                                const uint32_t a_t = tmem_base + (uint32_t)(RU_A_COL0 + (kb * 4 + k) * 8);   // 16 k = 8 columns
+                                const uint32_t acc = (kb | k) ? 1u : 0u;
+                                asm volatile(
+                                    "{\n\t.reg .pred p;\n\t"
+                                    "setp.ne.b32 p, %4, 0;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                                    ::"r"(tmem_base), "r"(a_t), "l"(bd + adv), "r"(idesc), "r"(acc) : "memory");
+                            } else {
+                                ptx::umma_f16(tmem_base, ad + adv, bd + adv, idesc, (kb | k) ? 1u : 0u);
+                            }
                         }
                     }
                     ptx::umma_commit(acc_full);
@@ -213,7 +262,7 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
     __syncthreads();
     if (warp == 0) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, RU_TMEM_COLS);
+        ptx::tmem_dealloc(tmem_base, A_TMEM ? RU_TMEM_COLS_A : RU_TMEM_COLS);
     }
 }
 

@@ -30,10 +30,14 @@ constexpr bool UMMA_AVAILABLE = true;
 constexpr int UM_BM = 128;          // UMMA M (cta_group::1)
 constexpr int UM_BK = 64;           // fp16 elements per k-block = one 128-byte swizzle row
 
-template <int BN> struct UmmaCfg {
-    static constexpr int STAGES = (BN == 256) ? 2 : 3;
+// CG = CTAs per tile: 1 (M = 128, tcgen05 cta_group::1) or 2 (a CTA pair computes a 256 x BN tile with
+// cta_group::2 MMAs: each CTA stages its own 128 rows of A and HALF of the B tile, so the L2->SM operand
+// traffic per flop is half that of two independent CTAs).
+template <int BN, int CG = 1> struct UmmaCfg {
+    static constexpr int B_ROWS = BN / CG;                      // rows of the B tile staged by one CTA
+    static constexpr int STAGES = (B_ROWS == 256) ? 2 : 3;
     static constexpr int A_BYTES = UM_BM * 128;                 // one plane of A per stage
-    static constexpr int B_BYTES = BN * 128;
+    static constexpr int B_BYTES = B_ROWS * 128;
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
     static constexpr int TMEM_COLS = 2 * BN;                    // double-buffered accumulator
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * 4096 /*epilogue staging*/ + 1024 /*align slack*/ +
@@ -97,6 +101,35 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load whose completion bytes are counted on an mbarrier that may live in the PEER CTA of the pair
+// (`bar_cluster` is a shared::cluster address, e.g. from mapa)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier at the same shared offset in BOTH CTAs of the pair once the MMAs retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -124,6 +157,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// same load without the wait: the caller issues several and then one tcgen05.wait::ld
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+          "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]),
+          "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]),
+          "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
     asm volatile(
@@ -201,14 +246,16 @@ __device__ __forceinline__ void half_split_store4_fast(__half* hi_p, __half* lo_
 constexpr int UM_EPI_WARPS = 8;                 // two warps per TMEM lane quarter (column halves)
 constexpr int UM_THREADS = 64 + 32 * UM_EPI_WARPS;
 
-template <int BN, bool LN, bool OUT_HALF>
+template <int BN, bool LN, bool OUT_HALF, int CG = 1>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                  const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
                  const __grid_constant__ CUtensorMap mapC0, const __grid_constant__ CUtensorMap mapC1,
+                 const __grid_constant__ CUtensorMap mapR_hi, const __grid_constant__ CUtensorMap mapR_lo,
                  int M, int N, int K, int m_tile0, int m_tile_cnt, Epi ep) {
-    using Cfg = UmmaCfg<BN>;
+    using Cfg = UmmaCfg<BN, CG>;
     constexpr int STAGES = Cfg::STAGES;
+    static_assert(CG == 1 || (CG == 2 && !LN && BN == 256), "pair tiles: 256 x 256, no LayerNorm epilogue");
     // 128B-swizzled operand tiles need 1024-byte alignment.  The kernel has no static shared memory,
     // so the dynamic window starts at shared offset 0; keeping the pointer un-cast preserves the
     // shared address space (LDS/STS instead of generic LD/ST for the epilogue staging).
@@ -221,23 +268,34 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]       MMA -> epilogue
     uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* rfull_bar = bars + 2 * STAGES + 5;  //           LN: residual tile landed in the ring (TMA -> epilogue)
     float* row_stat = reinterpret_cast<float*>(bars + 2 * STAGES + 6);   // LN: [2 halves][128 rows] partials, then mean/rstd
+    // LN fast path (no dropout): after a tile's last k-block the operand ring is idle, so the producer parks the
+    // residual tile there (128 KB, the same 64-column swizzled boxes the GEMMs read xa / xb with) and the
+    // epilogue stages its output boxes in the ring's last 64 KB; both stages go back to the producer when the
+    // tile's epilogue is done.
+    const bool ln_ring = LN && !(ep.drop_p > 0.f);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (N + BN - 1) / BN;
-    const int total_tiles = n_tiles * m_tile_cnt;              // m-tiles [m_tile0, m_tile0 + m_tile_cnt)
+    const int total_tiles = n_tiles * (m_tile_cnt / CG);       // m-tiles [m_tile0, m_tile0 + m_tile_cnt), CG per tile
     const int num_kb = K / UM_BK;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;   // rank 0 = leader: issues the pair's MMAs
+    const int grp = blockIdx.x / CG, n_grp = gridDim.x / CG;   // persistent loop over tiles, one CTA group per tile
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&mapA_hi); ptx::prefetch_tmap(&mapA_lo);
         ptx::prefetch_tmap(&mapB_hi); ptx::prefetch_tmap(&mapB_lo);
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], UM_EPI_WARPS); }
+        // the accumulator of a pair is released by the epilogue warps of BOTH CTAs (on the leader's barrier)
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], UM_EPI_WARPS * CG); }
+        ptx::mbar_init(rfull_bar, 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 1) ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == 1) { if constexpr (CG == 2) ptx::tmem_alloc2(tmem_slot, Cfg::TMEM_COLS); else ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS); }
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) { cluster_arrive(); cluster_wait(); }   // the peer's barriers exist before anything signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 #define TIP_TS(i) do { if (ep.tbuf && blockIdx.x == 0 && lane == 0) ep.tbuf[i] = ptx::globaltimer_ns(); } while (0)
@@ -246,28 +304,58 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m0 = (m_tile0 + tile / n_tiles) * UM_BM, n0 = (tile % n_tiles) * BN;
+            int stage = 0;
+            uint32_t uses[STAGES];                 // fills of each stage so far (k-blocks and residual tiles)
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) uses[s] = 0;
+            if constexpr (LN) { ptx::prefetch_tmap(&mapR_hi); ptx::prefetch_tmap(&mapR_lo); }
+            for (int tile = grp; tile < total_tiles; tile += n_grp) {
+                const int m0 = (m_tile0 + (tile / n_tiles) * CG + (int)cta_rank) * UM_BM;
+                const int n0 = (tile % n_tiles) * BN + (int)cta_rank * Cfg::B_ROWS;      // this CTA's slice of the B tile
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_wait(&empty_bar[stage], (uses[stage] & 1u) ^ 1u);
+                    uses[stage]++;
                     uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
-                    ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    ptx::tma_load_2d(s, &mapA_hi, &full_bar[stage], kb * UM_BK, m0);
-                    ptx::tma_load_2d(s + Cfg::A_BYTES, &mapA_lo, &full_bar[stage], kb * UM_BK, m0);
-                    ptx::tma_load_2d(s + 2 * Cfg::A_BYTES, &mapB_hi, &full_bar[stage], kb * UM_BK, n0);
-                    ptx::tma_load_2d(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, &full_bar[stage], kb * UM_BK, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if constexpr (CG == 2) {
+                        // both CTAs' bytes are counted on the LEADER's full barrier (it expects 2 stages' worth)
+                        const uint32_t fb = map_to_cta(ptx::smem_u32(&full_bar[stage]), 0u);
+                        if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                        ptx::tma_load_2d_pair(s, &mapA_hi, fb, kb * UM_BK, m0);
+                        ptx::tma_load_2d_pair(s + Cfg::A_BYTES, &mapA_lo, fb, kb * UM_BK, m0);
+                        ptx::tma_load_2d_pair(s + 2 * Cfg::A_BYTES, &mapB_hi, fb, kb * UM_BK, n0);
+                        ptx::tma_load_2d_pair(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, fb, kb * UM_BK, n0);
+                    } else {
+                        ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        ptx::tma_load_2d(s, &mapA_hi, &full_bar[stage], kb * UM_BK, m0);
+                        ptx::tma_load_2d(s + Cfg::A_BYTES, &mapA_lo, &full_bar[stage], kb * UM_BK, m0);
+                        ptx::tma_load_2d(s + 2 * Cfg::A_BYTES, &mapB_hi, &full_bar[stage], kb * UM_BK, n0);
+                        ptx::tma_load_2d(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, &full_bar[stage], kb * UM_BK, n0);
+                    }
+                    if (++stage == STAGES) stage = 0;
+                }
+                if constexpr (LN) {
+                    if (ln_ring) {
+                        // residual tile [128 rows x 256 cols] hi + lo -> ring bytes [0, 128 KB): box (plane p, column
+                        // block cb) at (p * 4 + cb) * 16 KB.  Needs the whole ring: every stage must have been read.
+#pragma unroll
+                        for (int s2 = 0; s2 < STAGES; ++s2) { ptx::mbar_wait(&empty_bar[s2], (uses[s2] & 1u) ^ 1u); uses[s2]++; }
+                        ptx::mbar_expect_tx(rfull_bar, 8 * Cfg::A_BYTES);
+#pragma unroll
+                        for (int cb = 0; cb < 4; ++cb) {
+                            ptx::tma_load_2d(smem + cb * Cfg::A_BYTES, &mapR_hi, rfull_bar, cb * UM_BK, m0);
+                            ptx::tma_load_2d(smem + (4 + cb) * Cfg::A_BYTES, &mapR_lo, rfull_bar, cb * UM_BK, m0);
+                        }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(UM_BM, BN);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(UM_BM * CG, BN);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = grp; tile < total_tiles; tile += n_grp, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -284,14 +372,22 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
 #pragma unroll
                     for (int k = 0; k < UM_BK / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 16 fp16 = 32 bytes along K
-                        ptx::umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-                        ptx::umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                        ptx::umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+                        if constexpr (CG == 2) {
+                            ptx::umma_f16_pair(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                            ptx::umma_f16_pair(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                            ptx::umma_f16_pair(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+                        } else {
+                            ptx::umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                            ptx::umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                            ptx::umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+                        }
                     }
-                    ptx::umma_commit(&empty_bar[stage]);          // smem stage free once these MMAs retire
+                    // smem stage free (in both CTAs of a pair) once these MMAs retire
+                    if constexpr (CG == 2) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tfull_bar[as]);                 // accumulator complete
+                // accumulator complete (each CTA's epilogue reads its own 128 rows from its own TMEM)
+                if constexpr (CG == 2) ptx::umma_commit_pair(&tfull_bar[as]); else ptx::umma_commit(&tfull_bar[as]);
                 if (it == 0) TIP_TS(2);
             }
         }
@@ -307,10 +403,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         const float osc = OUT_HALF ? ACT_SCALE : 1.f;             // output planes hold ACT_SCALE * x
         const float relu_floor = ep.relu ? 0.f : -INFINITY;
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = grp; tile < total_tiles; tile += n_grp, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int m0 = (m_tile0 + tile / n_tiles) * UM_BM, n0 = (tile % n_tiles) * BN;
+            const int m0 = (m_tile0 + (tile / n_tiles) * CG + (int)cta_rank) * UM_BM, n0 = (tile % n_tiles) * BN;
             const int rbase = m0 + quarter * 32;                  // first row of this warp
             // lean path: full tile, vector stores, no dropout (warp-uniform); everything else -> slow path
             const bool fast = (m0 + UM_BM <= M) && (n0 + BN <= N) && vec_ok && !(ep.drop_p > 0.f) && !(ep.dbg & 7);
@@ -465,6 +561,123 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
             } else {
                 // LayerNorm epilogue: out = LN(acc*asc + bias [dropout] + residual) * gamma + beta, BN == 256
                 // == the whole row.  Residual and output are FP16 hi/lo planes of ACT_SCALE * x.
+                if (ln_ring) {
+                    // ---- fast path: thread = accumulator row, its 128 columns stay in registers after ONE TMEM read ----
+                    // residual: from the swizzled boxes the producer parked in the ring; bias / gamma / beta: from
+                    // shared memory (the kernel runs with ~3 KB of L1, so every __ldg would be an L2 round trip);
+                    // output: 32x32 boxes staged in the ring's tail (two 4 KB buffers per warp) and TMA-stored.
+                    float* cvec = staging;                            // [0,256) bias, [256,512) gamma*16, [512,768) beta*16
+                    if (it == 0) {
+                        const int t = (int)threadIdx.x - 64;          // 0..255 among the epilogue threads
+                        cvec[t] = __ldg(ep.bias + t);
+                        cvec[256 + t] = __ldg(ep.gamma + t) * ACT_SCALE;
+                        cvec[512 + t] = __ldg(ep.beta + t) * ACT_SCALE;
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                    }
+                    const int trow = quarter * 32 + lane;             // row within the tile
+                    const int col0 = half * (BN / 2);
+                    float x[BN / 2];
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) ptx::tmem_ld32_nowait(t_acc + c * 32, *reinterpret_cast<float(*)[32]>(&x[c * 32]));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // the accumulator is in registers: hand the TMEM buffer back to the MMA warp now
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+                    ptx::mbar_wait(rfull_bar, (uint32_t)(it & 1));    // residual tile landed (issued right after the last k-block)
+                    float rsum = 0.f;
+                    const uint8_t* rrow = smem + trow * 128;          // this row inside every 16 KB box
+                    const int rsw = trow & 7;
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        const int cb = half * 2 + (c >> 1);           // 64-column box of this chunk
+                        const uint8_t* bh = rrow + cb * Cfg::A_BYTES;
+                        const uint8_t* bl = rrow + (4 + cb) * Cfg::A_BYTES;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {                 // 16-byte chunk = 8 columns
+                            const int pos = (((c & 1) * 4 + i) ^ rsw) << 4;
+                            const uint4 h4 = *reinterpret_cast<const uint4*>(bh + pos);
+                            const uint4 l4 = *reinterpret_cast<const uint4*>(bl + pos);
+                            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
+                            const uint32_t lw[4] = {l4.x, l4.y, l4.z, l4.w};
+                            const float4 b0 = *reinterpret_cast<const float4*>(cvec + col0 + c * 32 + i * 8);       // broadcast
+                            const float4 b1 = *reinterpret_cast<const float4*>(cvec + col0 + c * 32 + i * 8 + 4);
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                            for (int q2 = 0; q2 < 4; ++q2) {
+                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[q2]));
+                                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[q2]));
+                                const int j = c * 32 + i * 8 + q2 * 2;
+                                const float v0 = fmaf(hf.x + lf.x, 1.f / ACT_SCALE, fmaf(x[j], asc, bb[q2 * 2]));
+                                const float v1 = fmaf(hf.y + lf.y, 1.f / ACT_SCALE, fmaf(x[j + 1], asc, bb[q2 * 2 + 1]));
+                                x[j] = v0; x[j + 1] = v1;
+                                rsum += v0 + v1;
+                            }
+                        }
+                    }
+                    if (warp == 2 && it == 0) TIP_TS(4);
+                    row_stat[half * 128 + trow] = rsum;
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+                    const float mean = (row_stat[trow] + row_stat[128 + trow]) * (1.f / BN);
+                    float q2s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < BN / 2; ++j) { const float d = x[j] - mean; q2s = fmaf(d, d, q2s); }
+                    row_stat[256 + half * 128 + trow] = q2s;
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+                    const float var = (row_stat[256 + trow] + row_stat[256 + 128 + trow]) * (1.f / BN);
+                    const float ca = rsqrtf(var + 1e-5f), cb2 = -mean * ca;
+                    if (warp == 2 && it == 0) TIP_TS(5);
+                    uint8_t* obuf = smem + 8 * Cfg::A_BYTES + (warp - 2) * 8192;      // two 4 KB buffers (hi 2 KB | lo 2 KB)
+                    const int sw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        const int colb = col0 + c * 32;
+                        uint8_t* sbuf = obuf + (c & 1) * 4096;
+                        if (c >= 2) {                                 // the box stored two chunks ago has left this buffer
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 g0 = *reinterpret_cast<const float4*>(cvec + 256 + colb + 8 * j);
+                            const float4 g1 = *reinterpret_cast<const float4*>(cvec + 256 + colb + 8 * j + 4);
+                            const float4 e0 = *reinterpret_cast<const float4*>(cvec + 512 + colb + 8 * j);
+                            const float4 e1 = *reinterpret_cast<const float4*>(cvec + 512 + colb + 8 * j + 4);
+                            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                            const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                            uint32_t uh[4], ul[4];
+#pragma unroll
+                            for (int p2 = 0; p2 < 4; ++p2) {
+                                const int jj = c * 32 + 8 * j + 2 * p2;
+                                const float y0 = fmaf(fmaf(x[jj], ca, cb2), gg[2 * p2], ee[2 * p2]);
+                                const float y1 = fmaf(fmaf(x[jj + 1], ca, cb2), gg[2 * p2 + 1], ee[2 * p2 + 1]);
+                                float h0, h1, l0, l1;
+                                veltkamp11(y0, h0, l0); veltkamp11(y1, h1, l1);
+                                __half2 t2 = __floats2half2_rn(h0, h1); uh[p2] = *reinterpret_cast<uint32_t*>(&t2);
+                                t2 = __floats2half2_rn(l0, l1); ul[p2] = *reinterpret_cast<uint32_t*>(&t2);
+                            }
+                            const int off = lane * 64 + ((j ^ sw) << 4);
+                            *reinterpret_cast<uint4*>(sbuf + off) = make_uint4(uh[0], uh[1], uh[2], uh[3]);
+                            *reinterpret_cast<uint4*>(sbuf + 2048 + off) = make_uint4(ul[0], ul[1], ul[2], ul[3]);
+                        }
+                        ptx::fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&mapC0, sbuf, colb, rbase);
+                            ptx::tma_store_2d(&mapC1, sbuf + 2048, colb, rbase);
+                            ptx::bulk_commit();
+                        }
+                    }
+                    if (warp == 2 && it == 0) TIP_TS(6);
+                    // give the ring back to the producer once every warp's boxes have been read out of it
+                    if (lane == 0) ptx::bulk_wait_read0();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (threadIdx.x == 64) {
+#pragma unroll
+                        for (int s2 = 0; s2 < STAGES; ++s2) ptx::mbar_arrive(&empty_bar[s2]);
+                    }
+                    continue;                                         // tempty already arrived
+                }
                 const float inv_keep = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
                 const __half* res_hi = reinterpret_cast<const __half*>(ep.resid);
                 const __half* res_lo = reinterpret_cast<const __half*>(ep.resid_lo);
@@ -572,15 +785,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
             if (warp == 2 && it == 0) TIP_TS(6);
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);     // 8 arrivals free the accumulator
+            if (lane == 0) {                                      // 8 (x2 CTAs) arrivals free the accumulator
+                if constexpr (CG == 2) ptx::mbar_arrive_cluster(map_to_cta(ptx::smem_u32(&tempty_bar[as]), 0u));
+                else ptx::mbar_arrive(&tempty_bar[as]);
+            }
         }
     }
     if (warp >= 2 && lane == 0) ptx::bulk_wait0();                 // outstanding TMA stores of this warp
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) { cluster_arrive(); cluster_wait(); }   // neither CTA leaves while the pair's MMAs / arrivals can touch it
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if constexpr (CG == 2) ptx::tmem_dealloc2(tmem_base, Cfg::TMEM_COLS); else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
     if (warp == 2) TIP_TS(7);
 #undef TIP_TS
@@ -703,13 +920,19 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         cudaFuncSetAttribute(umma_gemm_kernel<256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<256, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256, 2>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<256, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256, 2>::SMEM_BYTES);
         mp.attrs_set = true;
     }
     return TIP_OK;
 }
 
-inline bool wide_mode() {
-    static const int v = getenv("TIP_BN256") ? atoi(getenv("TIP_BN256")) : 1;
+inline bool wide_mode() {      // experiment: 128 x 256 single-CTA tiles (measured: no gain, the 2-stage ring exposes latency)
+    static const int v = getenv("TIP_BN256") ? atoi(getenv("TIP_BN256")) : 0;
+    return v != 0;
+}
+inline bool pair_mode() {      // CTA-pair tiles for the wide non-LN GEMMs; TIP_PAIR=0 falls back to 128 x 128 single-CTA tiles
+    static const int v = getenv("TIP_PAIR") ? atoi(getenv("TIP_PAIR")) : 1;
     return v != 0;
 }
 
@@ -731,28 +954,46 @@ inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, c
     ep.tma_out = (C && C->valid && !getenv("TIP_NO_TMA_STORE")) ? 1 : 0;
     const CUtensorMap& c0 = C ? C->c0 : A->hi;
     const CUtensorMap& c1 = C ? C->c1 : A->lo;
+    // residual of the LayerNorm GEMMs, read through the same 64-column operand boxes the next GEMM uses
+    const UmmaOperand* Rm = (which == UG_OUT) ? &mp.a_xa : (which == UG_FF2) ? &mp.a_xb : A;
     const int m_tiles = m_tile_cnt >= 0 ? m_tile_cnt : (M + UM_BM - 1) / UM_BM;
     if (ln) {
         const int tiles = m_tiles;                                // BN = 256 = the whole row
         umma_gemm_kernel<256, true, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<256>::SMEM_BYTES, st>>>(
-            A->hi, A->lo, B->hi, B->lo, c0, c1, M, N, K, m_tile0, m_tiles, ep);
+            A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+    } else if (B256 && (N % 256) == 0 && (m_tiles % 2) == 0 && (m_tiles / 2) * (N / 256) >= 32 && pair_mode()) {
+        // CTA pairs (cta_group::2): 256 x 256 tiles, each CTA stages its 128 rows of A and half of B
+        const int units = (m_tiles / 2) * (N / 256);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * std::min(units, mp.num_sms / 2));
+        cfg.blockDim = dim3(UM_THREADS);
+        cfg.dynamicSmemBytes = UmmaCfg<256, 2>::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (ep.out_lo)
+            cudaLaunchKernelEx(&cfg, umma_gemm_kernel<256, false, true, 2>, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+        else
+            cudaLaunchKernelEx(&cfg, umma_gemm_kernel<256, false, false, 2>, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
     } else if (B256 && (N % 256) == 0 && m_tiles * (N / 256) >= mp.num_sms && wide_mode()) {
         // wide tiles: A is re-used over 256 columns (25 % less L2->SM operand traffic per flop)
         const int tiles = m_tiles * (N / 256);
         if (ep.out_lo)
             umma_gemm_kernel<256, false, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<256>::SMEM_BYTES, st>>>(
-                A->hi, A->lo, B256->hi, B256->lo, c0, c1, M, N, K, m_tile0, m_tiles, ep);
+                A->hi, A->lo, B256->hi, B256->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
         else
             umma_gemm_kernel<256, false, false><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<256>::SMEM_BYTES, st>>>(
-                A->hi, A->lo, B256->hi, B256->lo, c0, c1, M, N, K, m_tile0, m_tiles, ep);
+                A->hi, A->lo, B256->hi, B256->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
     } else {
         const int tiles = m_tiles * ((N + 127) / 128);
         if (ep.out_lo)
             umma_gemm_kernel<128, false, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<128>::SMEM_BYTES, st>>>(
-                A->hi, A->lo, B->hi, B->lo, c0, c1, M, N, K, m_tile0, m_tiles, ep);
+                A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
         else
             umma_gemm_kernel<128, false, false><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<128>::SMEM_BYTES, st>>>(
-                A->hi, A->lo, B->hi, B->lo, c0, c1, M, N, K, m_tile0, m_tiles, ep);
+                A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
     }
 }
 
