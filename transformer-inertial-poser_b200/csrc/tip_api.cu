@@ -20,13 +20,6 @@ std::string g_create_error;
 constexpr int CHUNK_WINDOWS = 1024;   // windows per pass through the workspace
 }  // namespace
 
-struct PipeCtx {
-    int n_in = 0, n_out = 0;
-    int in_row0[8], in_rows[8];          // conditioning row ranges (whole windows)
-    int out_tile0[8], out_tiles[8];      // head m-tile ranges
-    cudaEvent_t ev_in[8], ev_out[8];
-};
-
 // CUDA graphs of whole forwards, keyed by everything a captured launch sequence depends on.  A (shape,
 // pointer) combination is captured the second time it is seen (the first call runs eagerly and does all the
 // lazy initialisation: workspace, tensor maps, occupancy queries), then replayed: one graph launch instead
@@ -77,9 +70,6 @@ struct tip_model {
     // host-entry staging
     size_t host_cap = 0;      // windows*L capacity in rows
     float *h_in = nullptr, *h_out = nullptr, *d_ximu = nullptr, *d_xs = nullptr, *d_y = nullptr;
-    cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined host entry
-    cudaEvent_t ev_start = nullptr;
-    PipeCtx pipe;
 
     // streaming state
     int n_streams = 0, stream_len = 0;
@@ -238,10 +228,6 @@ extern "C" void tip_destroy(tip_model* m) {
     if (m->ws) cudaFree(m->ws);
     for (float* p : {m->d_ximu, m->d_xs, m->d_y}) if (p) cudaFree(p);
     for (float* p : {m->h_in, m->h_out}) if (p) cudaFreeHost(p);
-    if (m->s_in) {
-        cudaStreamDestroy(m->s_in); cudaStreamDestroy(m->s_out); cudaEventDestroy(m->ev_start);
-        for (int i = 0; i < 8; ++i) { cudaEventDestroy(m->pipe.ev_in[i]); cudaEventDestroy(m->pipe.ev_out[i]); }
-    }
     delete m;
 }
 
@@ -560,13 +546,10 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
     m->launches++;
 }
 
-// Host-entry pipelining (tip_forward_host): the H2D copy is split into window chunks, each conditioned as soon
-// as it lands; the head GEMM is split into m-tile ranges, each copied back as soon as it is done.  The body of
-// the forward runs on the whole batch in between.
 // One pass over <= CHUNK_WINDOWS windows.
 static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, float* y, int B, int L,
                          const float* keep_mask, float past_scale, const tip_dropout* drop,
-                         cudaStream_t st, const PipeCtx* pipe = nullptr) {
+                         cudaStream_t st) {
     const Dims& d = m->d;
     const PackOff& o = m->off;
     const float* W = m->blob;
@@ -597,15 +580,12 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
     m->st_names.clear();
     m->st_layers.clear();
     mark(m, st, "condition");
-    for (int ci = 0; ci < (pipe ? pipe->n_in : 1); ++ci) {
-        const int r0 = pipe ? pipe->in_row0[ci] : 0, nr = pipe ? pipe->in_rows[ci] : M;
-        if (pipe) cudaStreamWaitEvent(st, pipe->ev_in[ci], 0);       // this chunk's inputs have landed
-        const int64_t total = (int64_t)nr * (d.kin_pad / 8);
+    {
+        const int64_t total = (int64_t)M * (d.kin_pad / 8);
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
-        float* xo = umma ? reinterpret_cast<float*>(reinterpret_cast<__half*>(m->xin) + (size_t)r0 * d.kin_pad) : m->xin + (size_t)r0 * d.kin_pad;
-        float* xl = umma ? reinterpret_cast<float*>(reinterpret_cast<__half*>(lo_xin) + (size_t)r0 * d.kin_pad) : nullptr;
-        condition_kernel<<<blocks, 256, 0, st>>>(x_imu + (size_t)r0 * d.n_imu, x_s + (size_t)r0 * d.size_s,
-                                                 keep_mask ? keep_mask + (size_t)r0 * d.size_s : nullptr, past_scale, xo, xl, nr,
+        float* xo = m->xin;
+        float* xl = umma ? lo_xin : nullptr;
+        condition_kernel<<<blocks, 256, 0, st>>>(x_imu, x_s, keep_mask, past_scale, xo, xl, M,
                                                  d.n_imu, d.size_s, d.kin_pad, p_in, p_past, seed);
         m->launches++;
     }
@@ -625,8 +605,22 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
                 ep.tbuf = tb + 8 * (which + (layer > 0 ? 16 : 0));
                 g_tbuf = tb;
             }
-            umma_gemm(m->maps, which, layer, M, N, K, ep, ln, st, tile0, tiles);
-            m->launches++;
+            // small M: one CTA per 128-row tile would stream the whole weight matrix through a single SM (ff2: 17 us);
+            // split the columns over 4 CTAs (64-column tiles into the fp32 scratch) and normalise in a second, tiny kernel
+            static const int skinny_tiles = getenv("TIP_SKINNY_TILES") ? atoi(getenv("TIP_SKINNY_TILES")) : 8;
+            if (ln && (M + UM_BM - 1) / UM_BM <= skinny_tiles) {
+                Epi gp = ep;
+                gp.resid = gp.resid_lo = nullptr; gp.gamma = gp.beta = nullptr;
+                gp.out = m->gi; gp.out_lo = nullptr; gp.ldc = E;               // fp32 [rows][256]; gi is free until rnn_ih
+                umma_gemm(m->maps, which, layer, M, N, K, gp, false, st, 0, -1, true);
+                resid_ln_kernel<<<(M + 7) / 8, 256, 0, st>>>(m->gi, reinterpret_cast<const __half*>(ep.resid),
+                                                             reinterpret_cast<const __half*>(ep.resid_lo), ep.gamma, ep.beta,
+                                                             reinterpret_cast<__half*>(ep.out), reinterpret_cast<__half*>(ep.out_lo), 0, M);
+                m->launches += 2;
+            } else {
+                umma_gemm(m->maps, which, layer, M, N, K, ep, ln, st, tile0, tiles);
+                m->launches++;
+            }
         } else if (tiles >= 0) {
             const int r0 = tile0 * 128, nr = std::min(tiles * 128, M - r0);
             ep.out += (size_t)r0 * ep.ldc;
@@ -635,14 +629,9 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
             launch_sgemm(m, st, A, K, Wp, K, M, N, K, ep, ln);
         }
     };
-    // head GEMM, optionally in m-tile ranges with an event after each (pipelined D2H of the host entry)
     auto head = [&](int which, const float* A, int K) {
         Epi hp{}; hp.bias = W + o.bl; hp.out = y; hp.ldc = d.size_s;
-        if (!pipe) { gemm(which, 0, A, K, W + o.wl, d.size_s, hp, false); return; }
-        for (int j = 0; j < pipe->n_out; ++j) {
-            gemm(which, 0, A, K, W + o.wl, d.size_s, hp, false, pipe->out_tile0[j], pipe->out_tiles[j]);
-            cudaEventRecord(pipe->ev_out[j], st);
-        }
+        gemm(which, 0, A, K, W + o.wl, d.size_s, hp, false);
     };
     Epi ep{};
     // in_linear (+ folded head permutation)                                      reference :79-89
@@ -790,15 +779,6 @@ extern "C" int tip_forward_host(tip_model* m, const float* x_imu_h, const float*
         TIP_CUDA_TRY(m, cudaMallocHost(&m->h_out, cap * d.size_s * sizeof(float)));
         m->host_cap = cap;
     }
-    if (!m->s_in) {
-        TIP_CUDA_TRY(m, cudaStreamCreateWithFlags(&m->s_in, cudaStreamNonBlocking));
-        TIP_CUDA_TRY(m, cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
-        for (int i = 0; i < 8; ++i) {
-            TIP_CUDA_TRY(m, cudaEventCreateWithFlags(&m->pipe.ev_in[i], cudaEventDisableTiming));
-            TIP_CUDA_TRY(m, cudaEventCreateWithFlags(&m->pipe.ev_out[i], cudaEventDisableTiming));
-        }
-        TIP_CUDA_TRY(m, cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
-    }
     // pinned caller buffers are used in place; pageable ones go through the handle's pinned staging
     const float* src_imu = x_imu_h;
     const float* src_s = x_s_h;
@@ -809,62 +789,27 @@ extern "C" int tip_forward_host(tip_model* m, const float* x_imu_h, const float*
         memcpy(h_s, x_s_h, rows * d.size_s * sizeof(float));
         src_imu = h_imu; src_s = h_s;
     }
-    const bool stochastic = drop && (drop->in_dropout > 0.f || drop->past_state_dropout > 0.f || drop->encoder_dropout > 0.f);
     const bool out_pinned = is_pinned_host(y_h);
-    if (last_row_only || stochastic || B < 64 || B > CHUNK_WINDOWS) {
-        // simple path: one copy in, forward, one copy out
-        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->d_ximu, src_imu, rows * d.n_imu * sizeof(float), cudaMemcpyHostToDevice, st));
-        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->d_xs, src_s, rows * d.size_s * sizeof(float), cudaMemcpyHostToDevice, st));
-        int rc = tip_forward(m, m->d_ximu, m->d_xs, m->d_y, B, L, nullptr, 1.f, drop, st);
-        if (rc != TIP_OK) return rc;
-        const size_t out_rows = last_row_only ? (size_t)B : rows;
-        const float* dsrc = m->d_y;
-        if (last_row_only) {
-            last_row_kernel<<<(B * d.size_s + 255) / 256, 256, 0, st>>>(m->d_y, m->d_xs, B, L, d.size_s);
-            m->launches++;
-            dsrc = m->d_xs;
-        }
-        float* hdst = out_pinned ? y_h : m->h_out;
-        TIP_CUDA_TRY(m, cudaMemcpyAsync(hdst, dsrc, out_rows * d.size_s * sizeof(float), cudaMemcpyDeviceToHost, st));
-        TIP_CUDA_TRY(m, cudaStreamSynchronize(st));
-        if (!out_pinned) memcpy(y_h, m->h_out, out_rows * d.size_s * sizeof(float));
-        return TIP_OK;
-    }
-    // pipelined path
-    PipeCtx& pc = m->pipe;
-    const int n_chunks = 4;
-    pc.n_in = n_chunks;
-    const int M = (int)rows, m_tiles = (M + 127) / 128;
-    pc.n_out = std::min(n_chunks, m_tiles);
-    TIP_CUDA_TRY(m, cudaEventRecord(m->ev_start, st));          // earlier work on `st` may still read the staging buffers
-    TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->s_in, m->ev_start, 0));
-    TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->s_out, m->ev_start, 0));
-    for (int i = 0; i < n_chunks; ++i) {
-        const int w0 = (int)((int64_t)B * i / n_chunks), w1 = (int)((int64_t)B * (i + 1) / n_chunks);
-        pc.in_row0[i] = w0 * L;
-        pc.in_rows[i] = (w1 - w0) * L;
-        const size_t r0 = (size_t)w0 * L, nr = (size_t)(w1 - w0) * L;
-        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->d_ximu + r0 * d.n_imu, src_imu + r0 * d.n_imu, nr * d.n_imu * sizeof(float), cudaMemcpyHostToDevice, m->s_in));
-        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->d_xs + r0 * d.size_s, src_s + r0 * d.size_s, nr * d.size_s * sizeof(float), cudaMemcpyHostToDevice, m->s_in));
-        TIP_CUDA_TRY(m, cudaEventRecord(pc.ev_in[i], m->s_in));
-    }
-    for (int j = 0; j < pc.n_out; ++j) {
-        pc.out_tile0[j] = (int)((int64_t)m_tiles * j / pc.n_out);
-        pc.out_tiles[j] = (int)((int64_t)m_tiles * (j + 1) / pc.n_out) - pc.out_tile0[j];
-    }
-    m->launches = 0;
-    int rc = forward_chunk(m, m->d_ximu, m->d_xs, m->d_y, B, L, nullptr, 1.f, drop, st, &pc);
+    // one copy in per tensor, the forward (a CUDA-graph replay from the second call on: the staging addresses are
+    // stable), one copy out.  Measured on B200 (B = 256): H2D 167 us + forward 562 us + D2H 98 us; cutting the copies
+    // into parts to overlap them with the first / last kernels costs more per extra copy (~25 us of DMA set-up and
+    // stream hand-over each) than the ~50 us of overlap it can win, and running the batch as two concurrent half
+    // forwards does not help either (the kernels already fill the GPU) -- so the copies stay whole.
+    TIP_CUDA_TRY(m, cudaMemcpyAsync(m->d_ximu, src_imu, rows * d.n_imu * sizeof(float), cudaMemcpyHostToDevice, st));
+    TIP_CUDA_TRY(m, cudaMemcpyAsync(m->d_xs, src_s, rows * d.size_s * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = tip_forward(m, m->d_ximu, m->d_xs, m->d_y, B, L, nullptr, 1.f, drop, st);
     if (rc != TIP_OK) return rc;
-    float* hdst = out_pinned ? y_h : m->h_out;
-    for (int j = 0; j < pc.n_out; ++j) {
-        const size_t r0 = (size_t)pc.out_tile0[j] * 128;
-        const size_t nr = std::min((size_t)pc.out_tiles[j] * 128, rows - r0);
-        TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->s_out, pc.ev_out[j], 0));
-        TIP_CUDA_TRY(m, cudaMemcpyAsync(hdst + r0 * d.size_s, m->d_y + r0 * d.size_s, nr * d.size_s * sizeof(float), cudaMemcpyDeviceToHost, m->s_out));
+    const size_t out_rows = last_row_only ? (size_t)B : rows;
+    const float* dsrc = m->d_y;
+    if (last_row_only) {
+        last_row_kernel<<<(B * d.size_s + 255) / 256, 256, 0, st>>>(m->d_y, m->d_xs, B, L, d.size_s);
+        m->launches++;
+        dsrc = m->d_xs;
     }
-    TIP_CUDA_TRY(m, cudaStreamSynchronize(m->s_out));
+    float* hdst = out_pinned ? y_h : m->h_out;
+    TIP_CUDA_TRY(m, cudaMemcpyAsync(hdst, dsrc, out_rows * d.size_s * sizeof(float), cudaMemcpyDeviceToHost, st));
     TIP_CUDA_TRY(m, cudaStreamSynchronize(st));
-    if (!out_pinned) memcpy(y_h, m->h_out, rows * d.size_s * sizeof(float));
+    if (!out_pinned) memcpy(y_h, m->h_out, out_rows * d.size_s * sizeof(float));
     return TIP_OK;
 }
 

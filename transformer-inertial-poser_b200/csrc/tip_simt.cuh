@@ -764,6 +764,50 @@ imu_push_kernel(const float* __restrict__ raw_new, float* __restrict__ raw_ring,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Un-fused residual + LayerNorm of the skinny-M path (tcgen05 engine, M <= a few row tiles): the GEMM wrote
+// pre = acc + bias as fp32 [rows][256]; out = LN(pre + residual) * gamma + beta, residual and output being FP16 hi/lo
+// planes of ACT_SCALE * x.  One warp per row, 8 columns per lane, fully coalesced.
+__global__ void __launch_bounds__(256)
+resid_ln_kernel(const float* __restrict__ pre, const __half* __restrict__ res_hi, const __half* __restrict__ res_lo,
+                const float* __restrict__ gamma, const float* __restrict__ beta,
+                __half* __restrict__ out_hi, __half* __restrict__ out_lo, int row0, int rows) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
+    if (r >= rows) return;
+    const size_t base = (size_t)(row0 + r) * E + lane * 8;
+    const float4 p0 = *reinterpret_cast<const float4*>(pre + base), p1 = *reinterpret_cast<const float4*>(pre + base + 4);
+    const uint4 h4 = *reinterpret_cast<const uint4*>(res_hi + base), l4 = *reinterpret_cast<const uint4*>(res_lo + base);
+    float x[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+        const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+        x[2 * i] = fmaf(hf.x + lf.x, 1.f / ACT_SCALE, x[2 * i]);
+        x[2 * i + 1] = fmaf(hf.y + lf.y, 1.f / ACT_SCALE, x[2 * i + 1]);
+        sum += x[2 * i] + x[2 * i + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.f / E);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = x[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / E) + 1e-5f);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + lane * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + lane * 8 + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    __half hh[8], ll[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) half_split(fmaf((x[i] - mean) * rstd, gg[i], bb[i]) * ACT_SCALE, hh[i], ll[i]);
+    *reinterpret_cast<uint4*>(out_hi + base) = *reinterpret_cast<const uint4*>(hh);
+    *reinterpret_cast<uint4*>(out_lo + base) = *reinterpret_cast<const uint4*>(ll);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row N3: the model-visible part of RTRunnerMin.step AFTER the model call, on the device
 // (real_time_runner_minimal.py:87-112 smooth_and_split_s_c, :150-167 state assembly, :78-85/:196
 // record_state_aa_and_c; data_utils.py:164-187; fairmotion A2R / R2A = scipy Rotation).  One warp per

@@ -35,7 +35,7 @@ constexpr int UM_BK = 64;           // fp16 elements per k-block = one 128-byte 
 // traffic per flop is half that of two independent CTAs).
 template <int BN, int CG = 1> struct UmmaCfg {
     static constexpr int B_ROWS = BN / CG;                      // rows of the B tile staged by one CTA
-    static constexpr int STAGES = (B_ROWS == 256) ? 2 : 3;
+    static constexpr int STAGES = (B_ROWS == 256) ? 2 : (B_ROWS == 64) ? 4 : 3;
     static constexpr int A_BYTES = UM_BM * 128;                 // one plane of A per stage
     static constexpr int B_BYTES = B_ROWS * 128;
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
@@ -811,6 +811,8 @@ struct UmmaMaps {
     UmmaOperand a_xin, a_xa, a_xb, a_att, a_hid, a_hs;                    // activations (box 32 x 128)
     UmmaOperand w_in, w_qkv[MAX_LAYERS], w_o[MAX_LAYERS], w_1[MAX_LAYERS], w_2[MAX_LAYERS], w_ih, w_l;
     UmmaOperand w_qkv256[MAX_LAYERS], w_1256[MAX_LAYERS], w_ih256;        // 256-row boxes of the same planes (wide tiles)
+    UmmaOperand w_o64[MAX_LAYERS], w_264[MAX_LAYERS];                     // 64-row boxes (skinny-M LayerNorm GEMMs, 4 CTAs per row tile)
+    UmmaOutput o_pre;                                                      // fp32 [rows][256] scratch of the un-fused LayerNorm path
     UmmaOutput o_xa, o_xb, o_hid, o_qkv, o_gi;                             // TMA-store targets
     UmmaOperand w_hh;                                                      // resident A operand of the recurrence (box 64 x 64)
     int num_sms = 148;
@@ -881,6 +883,7 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
     outp(mp.o_hid, hid, plane_f, F, true);
     outp(mp.o_qkv, qkv, (size_t)cap_rows * 3 * E, 3 * E, true);      // FP16 hi/lo planes of 16*q|k|v for the mma attention
     outp(mp.o_gi, gi, 0, R, false);
+    outp(mp.o_pre, gi, 0, E, false);         // same memory as gi (free until rnn_ih), viewed as [rows][256]
     // activation planes: hi at the start of the buffer, lo `plane` halves later (same bytes as one fp32 plane)
     auto act = [&](UmmaOperand& op, const float* p, size_t plane, int cols) {
         const __half* h = reinterpret_cast<const __half*>(p);
@@ -903,6 +906,8 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         wgt(mp.w_o[l], L.wo_hi, L.wo_lo, E, E, 256);
         wgt(mp.w_1[l], L.w1_hi, L.w1_lo, F, E, 128);
         wgt(mp.w_qkv256[l], L.wqkv_hi, L.wqkv_lo, 3 * E, E, 256);
+        wgt(mp.w_o64[l], L.wo_hi, L.wo_lo, E, E, 64);
+        wgt(mp.w_264[l], L.w2_hi, L.w2_lo, E, F, 64);
         wgt(mp.w_1256[l], L.w1_hi, L.w1_lo, F, E, 256);
         wgt(mp.w_2[l], L.w2_hi, L.w2_lo, E, F, 256);
     }
@@ -920,6 +925,7 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         cudaFuncSetAttribute(umma_gemm_kernel<256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256, 2>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256, 2>::SMEM_BYTES);
         mp.attrs_set = true;
@@ -931,13 +937,15 @@ inline bool wide_mode() {      // experiment: 128 x 256 single-CTA tiles (measur
     static const int v = getenv("TIP_BN256") ? atoi(getenv("TIP_BN256")) : 0;
     return v != 0;
 }
-inline bool pair_mode() {      // CTA-pair tiles for the wide non-LN GEMMs; TIP_PAIR=0 falls back to 128 x 128 single-CTA tiles
-    static const int v = getenv("TIP_PAIR") ? atoi(getenv("TIP_PAIR")) : 1;
+inline bool pair_mode() {      // experiment (TIP_PAIR=1): CTA-pair tiles for the wide non-LN GEMMs.  Measured: the mainloop becomes MMA-bound (4.2 us per 256x256 tile) but the 128x256 epilogue per CTA (5 us) is then the critical path -> no gain over 128x128 single-CTA tiles
+    static const int v = getenv("TIP_PAIR") ? atoi(getenv("TIP_PAIR")) : 0;
     return v != 0;
 }
 
+// skinny: (LayerNorm GEMMs at small M) run the plain GEMM with 64-column tiles -- 4 CTAs per row tile instead of 1 --
+// into the fp32 scratch `o_pre`; the caller follows with resid_ln_kernel.
 inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, const Epi& ep_in, bool ln,
-                      cudaStream_t st, int m_tile0 = 0, int m_tile_cnt = -1) {
+                      cudaStream_t st, int m_tile0 = 0, int m_tile_cnt = -1, bool skinny = false) {
     const UmmaOperand *A = nullptr, *B = nullptr, *B256 = nullptr;
     const UmmaOutput* C = nullptr;
     switch (which) {
@@ -957,6 +965,14 @@ inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, c
     // residual of the LayerNorm GEMMs, read through the same 64-column operand boxes the next GEMM uses
     const UmmaOperand* Rm = (which == UG_OUT) ? &mp.a_xa : (which == UG_FF2) ? &mp.a_xb : A;
     const int m_tiles = m_tile_cnt >= 0 ? m_tile_cnt : (M + UM_BM - 1) / UM_BM;
+    if (skinny) {
+        const UmmaOperand* B64 = (which == UG_OUT) ? &mp.w_o64[layer] : &mp.w_264[layer];
+        ep.tma_out = (mp.o_pre.valid && !getenv("TIP_NO_TMA_STORE")) ? 1 : 0;
+        const int tiles = m_tiles * (N / 64);
+        umma_gemm_kernel<64, false, false><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<64>::SMEM_BYTES, st>>>(
+            A->hi, A->lo, B64->hi, B64->lo, mp.o_pre.c0, mp.o_pre.c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+        return;
+    }
     if (ln) {
         const int tiles = m_tiles;                                // BN = 256 = the whole row
         umma_gemm_kernel<256, true, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<256>::SMEM_BYTES, st>>>(

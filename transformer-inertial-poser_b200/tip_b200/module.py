@@ -224,7 +224,7 @@ class TF_RNN_Past_State(nn.Module):
         """``model(x_imu.cuda(), x_s.cuda()).cpu()`` in one C call with host (numpy / CPU tensor)
         buffers: H2D, forward, D2H, stream sync (real_time_runner_minimal.py:149).  Runs on the
         device the parameters live on.  Pinned buffers (``tensor.pin_memory()``) are used in place and,
-        for B >= 64, the copies are pipelined against the conditioning and head kernels; pageable
+        the forward is a CUDA-graph replay from the second call on; pageable
         buffers go through the handle's pinned staging.  ``out``: optional pre-allocated CPU tensor."""
         dev = next(self.parameters()).device
         if dev.type != "cuda":
@@ -260,6 +260,12 @@ class TF_RNN_Past_State(nn.Module):
         dev = next(self.parameters()).device
         h = self._ensure(dev)
         capi.check(self._lib, h, self._lib.tip_set_gemm_engine(h, int(engine)), "tip_set_gemm_engine")
+
+    def set_use_graphs(self, enable: bool):
+        """CUDA-graph replay of repeated forwards / streaming frames (tip_set_use_graphs); on by default."""
+        dev = next(self.parameters()).device
+        h = self._ensure(dev)
+        capi.check(self._lib, h, self._lib.tip_set_use_graphs(h, int(enable)), "tip_set_use_graphs")
 
     def algorithmic_cost(self, B: int, L: int):
         """(bytes, flops) of one forward as SURVEY.md 8d defines them."""
