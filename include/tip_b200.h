@@ -142,9 +142,11 @@ int  tip_stream_step_raw(tip_model* m, const float* raw_imu, const float* s_row,
  *
  * tip_stream_set_state: the first x_s row of every stream, (S, size_s) fp32 = record_state_aa_and_c(s_init,
  * zeros) as the runner's constructor appends it (:47); call after tip_stream_reset.
- * tip_stream_state_width: W = 57 + (size_s - 111) doubles per stream:
- *   state[0:57] = s_t[3:60] (root axis-angle, 17 joint axis-angles in Nimble order, root velocity),
- *   state[57:W] = c_t (per SBP: flag in {0,1}, offset xyz in metres).
+ * tip_stream_state_width: W = 60 + n_c doubles per stream, n_c = size_s - 111:
+ *   state[0:57]       = s_t[3:60] (root axis-angle, 17 joint axis-angles in Nimble order, root velocity as
+ *                       stored by :158/:166, i.e. averaged with the previous frame's),
+ *   state[57:57+n_c]  = c_t (per SBP: flag in {0,1}, offset xyz in metres),
+ *   state[57+n_c:W]   = root_v, the filtered but not yet averaged root velocity that :159 integrates.
  * tip_stream_step_closed: raw_imu (S, 72) fp32 as tip_stream_step_raw; state_out (S, W) float64 (host or
  * device per rows_on_host).  *produced = 0 during the runner's 5 warm-up calls (state_out untouched).
  * y_override (optional, same residence as raw_imu): (S, size_s) fp32 used INSTEAD of the model's last

@@ -358,7 +358,7 @@ class PostProcessor:
         self.buf = []
         self.last_tail = None                                           # last_s[6:60]
 
-    def step(self, y_last, root_R_row):
+    def step(self, y_last, root_R_row, with_root_v=False):
         y = np.array(y_last, dtype=np.float32)                          # the buffer keeps THIS array (:91)
         self.buf.append(y)
         if len(self.buf) >= 6:                                          # :93-96
@@ -372,7 +372,8 @@ class PostProcessor:
         c_t[1::4] /= 5.0
         c_t[2::4] /= 5.0
         c_t[3::4] /= 5.0
-        root_v = st[-3:]
+        root_v = st[-3:]                                                # :154 (integrated into the root position at :159)
+        root_v_out = np.array(root_v, dtype=np.float64)
         st_aa = rot6_to_aa(st[:-3])                                     # :155
         tail = np.zeros(N_DOFS - 6 + 3)                                 # s_t[6:60]
         tail[:N_DOFS - 6] = st_aa[3:]                                   # :160
@@ -383,4 +384,6 @@ class PostProcessor:
         self.last_tail = tail.copy()
         s = np.concatenate((root_aa, tail))                             # s_t[3:60]
         row = np.concatenate((aa_to_rotmat(s[:54].reshape(-1, 3))[:, :, :2].reshape(-1), s[54:57], c_t))
+        if with_root_v:
+            return s, np.array(c_t, dtype=np.float64), row, root_v_out
         return s, np.array(c_t, dtype=np.float64), row

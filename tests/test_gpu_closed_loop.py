@@ -39,6 +39,8 @@ def test_post_step_teacher_forced_matches_reference_runner(trace, model):
     first five calls, which the reference computes in float32 -- see PostProcessor.step)."""
     sess = StreamSession(model, n_streams=1)
     sess.set_state(trace["s_init"])
+    assert sess.state_width == 80
+    pp = O.PostProcessor()
     k = 0
     for t in range(trace["imu"].shape[0]):
         yo = trace["y_last"][k][None] if t >= 5 else None
@@ -48,7 +50,9 @@ def test_post_step_teacher_forced_matches_reference_runner(trace, model):
             continue
         tol = 2e-6 if k < 5 else 1e-9
         np.testing.assert_allclose(st[0, :57], trace["qdq"][t][3:60], atol=tol, err_msg=f"call {t}")
-        np.testing.assert_allclose(st[0, 57:], trace["ct"][t], atol=tol, err_msg=f"call {t}")
+        np.testing.assert_allclose(st[0, 57:77], trace["ct"][t], atol=tol, err_msg=f"call {t}")
+        _, _, _, rv = pp.step(trace["y_last"][k], trace["x_imu_last"][k][:9], with_root_v=True)
+        np.testing.assert_allclose(st[0, 77:80], rv, atol=tol, err_msg=f"root_v, call {t}")
         k += 1
     # the rows fed back on the device are what the reference runner appended to s_and_c_in_buffer
     win_s = sess.window("win_s").cpu().numpy()[0]
@@ -70,8 +74,8 @@ def test_closed_loop_tracks_reference_runner(trace, model):
             assert st is None
             continue
         worst = max(worst, np.abs(st[0, :57] - trace["qdq"][t][3:60]).max())
-        flips += int((st[0, 57::4] != trace["ct"][t][0::4]).sum())
-        np.testing.assert_allclose(st[0, 58::4], trace["ct"][t][1::4], atol=1e-3)
+        flips += int((st[0, 57:77:4] != trace["ct"][t][0::4]).sum())
+        np.testing.assert_allclose(st[0, 58:77:4], trace["ct"][t][1::4], atol=1e-3)
     assert worst < 1e-3, worst
     assert flips == 0, flips          # contact flags (logit > 0) agree on every frame of this trace
 

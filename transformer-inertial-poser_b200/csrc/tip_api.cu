@@ -833,7 +833,7 @@ extern "C" int tip_stream_reset(tip_model* m, int n_streams) {
     TIP_CUDA_TRY(m, cudaMalloc(&m->st_raw, S * IMU_RAW * sizeof(float)));
     TIP_CUDA_TRY(m, cudaMalloc(&m->acc_ring, S * ACC_WIN * 18 * sizeof(double)));
     TIP_CUDA_TRY(m, cudaMallocHost(&m->h_raw, S * IMU_RAW * sizeof(float)));
-    const size_t out_w = 57 + (d.size_s - 111);
+    const size_t out_w = 60 + (d.size_s - 111);
     TIP_CUDA_TRY(m, cudaMalloc(&m->fb_s, S * d.size_s * sizeof(float)));
     TIP_CUDA_TRY(m, cudaMalloc(&m->pp_ring, S * PP_TAPS * d.size_s * sizeof(double)));
     TIP_CUDA_TRY(m, cudaMalloc(&m->pp_last, S * PP_TAIL * sizeof(double)));
@@ -986,7 +986,7 @@ extern "C" int tip_stream_step_raw(tip_model* m, const float* raw_imu, const flo
 
 // ------------------------------------------------------------------------------------------------
 // Row N3: closed loop -- post-model step on the device, state row fed back without leaving the GPU.
-extern "C" int tip_stream_state_width(const tip_model* m) { return m ? 57 + (m->d.size_s - 111) : 0; }
+extern "C" int tip_stream_state_width(const tip_model* m) { return m ? 60 + (m->d.size_s - 111) : 0; }
 
 extern "C" int tip_stream_set_state(tip_model* m, const float* s_row0, int rows_on_host, void* stream_) {
     if (!m || !s_row0) return TIP_ERR_INVALID_ARG;
@@ -1018,7 +1018,7 @@ extern "C" int tip_stream_step_closed(tip_model* m, const float* raw_imu, const 
     const Dims& d = m->d;
     const size_t S = m->n_streams;
     const size_t n_i = S * d.n_imu, n_s = S * d.size_s, n_r = S * IMU_RAW;
-    const size_t out_w = 57 + (d.size_s - 111);
+    const size_t out_w = 60 + (d.size_s - 111);
     if (rows_on_host) {
         memcpy(m->h_raw, raw_imu, n_r * sizeof(float));
         TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_raw, m->h_raw, n_r * sizeof(float), cudaMemcpyHostToDevice, st));

@@ -9,7 +9,8 @@
 //   S  (48 x 40) = Q K^T : 11 causal 16x8 tiles x 3 products, K = 16 = head dim -> one k-step
 //   O  (48 x 16) = P V   : probabilities re-split to FP16 hi/lo in registers (the S accumulator
 //                          fragment of two adjacent key tiles IS the A fragment of the next MMA);
-//                          V fragments come from ldmatrix.trans on the row-major tile
+//                          V fragments come from ldmatrix.trans on the row-major tile; Q fragments come straight
+//                          from global memory
 // Softmax statistics are fp32 on the accumulator fragments (quad shuffles).  The contraction is 2 %
 // of the path's MACs; the kernel is bound by moving qkv in and o out, so everything goes through
 // shared memory in 256-byte-per-row coalesced pieces.
@@ -23,7 +24,10 @@ template <int HPB> struct AttnCfg {          // HPB heads per CTA (one warp each
     static constexpr int ROWB = HPB * HD * 2 + 16;          // bytes per row of a plane tile (+16 B pad: bank spread)
     static constexpr int QK_BYTES = MAXL * ROWB;
     static constexpr int V_BYTES = AM_VROWS * ROWB;
-    static constexpr int SMEM_BYTES = 4 * QK_BYTES + 2 * V_BYTES;
+    // K hi/lo + V hi/lo tiles; Q never touches shared memory (its fragments are 4-byte global loads that use every
+    // byte of their 32-byte sectors), which keeps a CTA of 8 heads at 47.9 KB: FOUR CTAs per SM, so the 512 CTAs of a
+    // 256-window batch are co-resident in one wave (with Q staged too it was 69.6 KB -> 3 per SM -> two waves).
+    static constexpr int SMEM_BYTES = 2 * QK_BYTES + 2 * V_BYTES;
 };
 
 __device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -41,31 +45,28 @@ __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint3
 }
 
 template <int AM_HPB>
-__global__ void __launch_bounds__(AM_HPB * 32)
+__global__ void __launch_bounds__(AM_HPB * 32, 1024 / (AM_HPB * 32) < 4 ? 1024 / (AM_HPB * 32) : 4)
 attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict__ qkv_lo,
                      __half* __restrict__ out_hi, __half* __restrict__ out_lo, int L, float drop_p, uint64_t seed) {
     constexpr int AM_ROWB = AttnCfg<AM_HPB>::ROWB, AM_QK_BYTES = AttnCfg<AM_HPB>::QK_BYTES, AM_V_BYTES = AttnCfg<AM_HPB>::V_BYTES;
     constexpr int CPR = AM_HPB * 2;                  // 16-byte chunks per row of a plane tile
     extern __shared__ __align__(16) uint8_t am_smem[];
-    uint8_t* sQh = am_smem;                          // [L][8 heads][16] halves
-    uint8_t* sQl = sQh + AM_QK_BYTES;
-    uint8_t* sKh = sQl + AM_QK_BYTES;
+    uint8_t* sKh = am_smem;                          // [L][8 heads][16] halves
     uint8_t* sKl = sKh + AM_QK_BYTES;
     uint8_t* sVh = sKl + AM_QK_BYTES;                // [48 keys][8 heads][16] halves, rows >= L zero
     uint8_t* sVl = sVh + AM_V_BYTES;
-    float* sO = reinterpret_cast<float*>(am_smem);   // [L][8 heads][16] fp32, aliases the Q planes after they are consumed
+    float* sO = reinterpret_cast<float*>(am_smem);   // [L][8 heads][16] fp32, aliases the K planes after they are consumed
 
     const int b = blockIdx.x, h0 = blockIdx.y * AM_HPB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const size_t rowbase = (size_t)b * L;
 
-    // ---- stage Q, K, V rows with cp.async (16 B = 8 dims of one head); V rows L..47 are zeroed ----
-    for (int i = tid; i < L * CPR * 6; i += AM_HPB * 32) {         // (row, {Qh,Ql,Kh,Kl,Vh,Vl}, chunk)
-        const int row = i / (6 * CPR), r = i - row * (6 * CPR), which = r / CPR, c = r - which * CPR;
-        const __half* src = ((which & 1) ? qkv_lo : qkv_hi) + (rowbase + row) * (3 * E) + (which >> 1) * E + h0 * HD + c * 8;
-        uint8_t* dst = (which == 0 ? sQh : which == 1 ? sQl : which == 2 ? sKh : which == 3 ? sKl : which == 4 ? sVh : sVl) +
-                       row * AM_ROWB + c * 16;
+    // ---- stage K, V rows with cp.async (16 B = 8 dims of one head); V rows L..47 are zeroed ----
+    for (int i = tid; i < L * CPR * 4; i += AM_HPB * 32) {         // (row, {Kh,Kl,Vh,Vl}, chunk)
+        const int row = i / (4 * CPR), r = i - row * (4 * CPR), which = r / CPR, c = r - which * CPR;
+        const __half* src = ((which & 1) ? qkv_lo : qkv_hi) + (rowbase + row) * (3 * E) + (1 + (which >> 1)) * E + h0 * HD + c * 8;
+        uint8_t* dst = (which == 0 ? sKh : which == 1 ? sKl : which == 2 ? sVh : sVl) + row * AM_ROWB + c * 16;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -73,21 +74,22 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
         const int plane = i & 1, c = (i >> 1) % CPR, row = L + (i >> 1) / CPR;
         *reinterpret_cast<uint4*>((plane ? sVl : sVh) + row * AM_ROWB + c * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
 
     // ---- per warp: head hl ----
     const int hl = warp;
-    uint32_t qa_hi[3][4], qa_lo[3][4];               // A fragments of Q (3 row tiles of 16)
+    // A fragments of Q (3 row tiles of 16) straight from the global planes; rows >= L are don't-care (clamped)
+    uint32_t qa_hi[3][4], qa_lo[3][4];
 #pragma unroll
     for (int mt = 0; mt < 3; ++mt) {
-        const int r0 = min(16 * mt + g, MAXL - 1), r1 = min(16 * mt + g + 8, MAXL - 1);   // rows >= L are don't-care
-        const int o0 = r0 * AM_ROWB + hl * 32 + t4 * 4, o1 = r1 * AM_ROWB + hl * 32 + t4 * 4;
-        qa_hi[mt][0] = *reinterpret_cast<const uint32_t*>(sQh + o0);      qa_lo[mt][0] = *reinterpret_cast<const uint32_t*>(sQl + o0);
-        qa_hi[mt][1] = *reinterpret_cast<const uint32_t*>(sQh + o1);      qa_lo[mt][1] = *reinterpret_cast<const uint32_t*>(sQl + o1);
-        qa_hi[mt][2] = *reinterpret_cast<const uint32_t*>(sQh + o0 + 16); qa_lo[mt][2] = *reinterpret_cast<const uint32_t*>(sQl + o0 + 16);
-        qa_hi[mt][3] = *reinterpret_cast<const uint32_t*>(sQh + o1 + 16); qa_lo[mt][3] = *reinterpret_cast<const uint32_t*>(sQl + o1 + 16);
+        const int r0 = min(16 * mt + g, L - 1), r1 = min(16 * mt + g + 8, L - 1);
+        const size_t o0 = (rowbase + r0) * (3 * E) + (h0 + hl) * HD + t4 * 2, o1 = (rowbase + r1) * (3 * E) + (h0 + hl) * HD + t4 * 2;
+        qa_hi[mt][0] = __ldg(reinterpret_cast<const uint32_t*>(qkv_hi + o0));     qa_lo[mt][0] = __ldg(reinterpret_cast<const uint32_t*>(qkv_lo + o0));
+        qa_hi[mt][1] = __ldg(reinterpret_cast<const uint32_t*>(qkv_hi + o1));     qa_lo[mt][1] = __ldg(reinterpret_cast<const uint32_t*>(qkv_lo + o1));
+        qa_hi[mt][2] = __ldg(reinterpret_cast<const uint32_t*>(qkv_hi + o0 + 8)); qa_lo[mt][2] = __ldg(reinterpret_cast<const uint32_t*>(qkv_lo + o0 + 8));
+        qa_hi[mt][3] = __ldg(reinterpret_cast<const uint32_t*>(qkv_hi + o1 + 8)); qa_lo[mt][3] = __ldg(reinterpret_cast<const uint32_t*>(qkv_lo + o1 + 8));
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
     uint32_t kb_hi[5][2], kb_lo[5][2];               // B fragments of K^T (5 key tiles of 8)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt) {
@@ -95,7 +97,7 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
         kb_hi[nt][0] = *reinterpret_cast<const uint32_t*>(sKh + o);      kb_lo[nt][0] = *reinterpret_cast<const uint32_t*>(sKl + o);
         kb_hi[nt][1] = *reinterpret_cast<const uint32_t*>(sKh + o + 16); kb_lo[nt][1] = *reinterpret_cast<const uint32_t*>(sKl + o + 16);
     }
-    __syncthreads();                                 // every warp holds its Q/K fragments: the Q planes may become sO
+    __syncthreads();                                 // every warp holds its K fragments: the K planes may become sO
 
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     // ldmatrix.trans row addresses of this lane: lanes 0-7 -> keys +0..7, lanes 8-15 -> keys +8..15

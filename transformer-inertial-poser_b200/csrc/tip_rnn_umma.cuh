@@ -35,12 +35,17 @@ constexpr int RU_B_KB_BYTES = 2 * RU_N * 128;         // 6 KB: one k-block of st
 constexpr int RU_B_BYTES = 8 * RU_B_KB_BYTES;         // 48 KB per parity
 constexpr int RU_SMEM_BYTES = RU_A_BYTES + 2 * RU_B_BYTES + 256;
 constexpr uint32_t RU_PUSH_BYTES = (RU_CTAS - 1) * RU_B_KB_BYTES;         // what the 7 peers deliver per step
-constexpr int RU_TMEM_COLS = 64;
+// RU_NACC independent accumulators (k-block kb -> accumulator kb % RU_NACC, 64 TMEM columns apart; the epilogue adds
+// the partial sums).  Experiment: with 4 accumulators the 32 MMAs of a step no longer form one dependent chain, yet
+// the issue phase stays 1.0 us (31 ns per M=128 x N=48 x K=16 MMA) -- like the A-in-TMEM variant this shows that the
+// single issuing thread, not the accumulate dependency or the shared-memory operand read, paces these small MMAs.
+constexpr int RU_NACC = 1;
+constexpr int RU_TMEM_COLS = 64 * RU_NACC;
 // A_TMEM variant: the W_hh slice lives in TENSOR MEMORY instead of shared memory (128 lanes x 256 32-bit
 // columns = 128 stacked rows x 512 fp16 k), so each MMA reads only the small h operand from shared memory;
 // the shared-memory read of the 4 KB A slice per MMA is what bounds the issue rate of the SS form.
 constexpr int RU_TMEM_COLS_A = 512;
-constexpr int RU_A_COL0 = 64;                        // first TMEM column of the A operand (D uses [0, 48))
+constexpr int RU_A_COL0 = 64 * RU_NACC;              // first TMEM column of the A operand (the accumulators come first)
 
 template <bool A_TMEM>
 __global__ void __cluster_dims__(RU_CTAS, 1, 1) __launch_bounds__(RU_THREADS, 1)
@@ -149,14 +154,15 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
                             const uint64_t adv = (uint64_t)((k * 32) >> 4);
                             if constexpr (A_TMEM) {
                                 const uint32_t a_t = tmem_base + (uint32_t)(RU_A_COL0 + (kb * 4 + k) * 8);   // 16 k = 8 columns
-                                const uint32_t acc = (kb | k) ? 1u : 0u;
+                                const uint32_t acc = (kb >= RU_NACC || k) ? 1u : 0u;
                                 asm volatile(
                                     "{\n\t.reg .pred p;\n\t"
                                     "setp.ne.b32 p, %4, 0;\n\t"
                                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                                    ::"r"(tmem_base), "r"(a_t), "l"(bd + adv), "r"(idesc), "r"(acc) : "memory");
+                                    ::"r"(tmem_base + (uint32_t)((kb % RU_NACC) * 64)), "r"(a_t), "l"(bd + adv), "r"(idesc), "r"(acc) : "memory");
                             } else {
-                                ptx::umma_f16(tmem_base, ad + adv, bd + adv, idesc, (kb | k) ? 1u : 0u);
+                                ptx::umma_f16(tmem_base + (uint32_t)((kb % RU_NACC) * 64), ad + adv, bd + adv, idesc,
+                                              (kb >= RU_NACC || k) ? 1u : 0u);
                             }
                         }
                     }
@@ -187,23 +193,29 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
                     if (tbuf && blockIdx.x == 0 && t == 20 && et == 0) tbuf[2] = ptx::globaltimer_ns();
                     ptx::tc_fence_after();
                     // columns [12ch, 12ch+12) (x h_hi) and [24+12ch, ...) (x h_lo) of this lane's stacked row
-                    uint32_t r0[12], r1[12];
-                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(12 * ch);
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]) : "r"(ta) : "memory");
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                 : "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]), "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11])
-                                 : "r"(ta + 4) : "memory");
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]) : "r"(ta + 24) : "memory");
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                 : "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]), "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11])
-                                 : "r"(ta + 28) : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    ptx::tc_fence_before();
                     float s[12];
 #pragma unroll
-                    for (int j = 0; j < 12; ++j) s[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                    for (int j = 0; j < 12; ++j) s[j] = 0.f;
+                    const uint32_t ta0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(12 * ch);
+#pragma unroll
+                    for (int a = 0; a < RU_NACC; ++a) {
+                        uint32_t r0[12], r1[12];
+                        const uint32_t ta = ta0 + (uint32_t)(a * 64);
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]) : "r"(ta) : "memory");
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]), "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11])
+                                     : "r"(ta + 4) : "memory");
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]) : "r"(ta + 24) : "memory");
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]), "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11])
+                                     : "r"(ta + 28) : "memory");
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int j = 0; j < 12; ++j) s[j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                    }
+                    ptx::tc_fence_before();
                     // fold the hi-row and lo-row lanes of a unit; lane half lh keeps windows 6lh..6lh+5
 #pragma unroll
                     for (int j = 0; j < 6; ++j) {

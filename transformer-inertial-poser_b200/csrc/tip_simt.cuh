@@ -816,7 +816,8 @@ resid_ln_kernel(const float* __restrict__ pre, const __half* __restrict__ res_hi
 // the normalisation / cross product of data_utils.py:170-172 run in float32 and :107-110 edit the
 // buffered row in place); both quirks are kept.  PyBullet FK and the SBP root correction (:169-194)
 // only produce the root translation, which is never fed back, and stay on the CPU.
-//   out_state[s] = [ s_t[3:60] (root aa from the IMU, 17 joint aa, root velocity) | c_t ]   (57 + n_c doubles)
+//   out_state[s] = [ s_t[3:60] (root aa from the IMU, 17 joint aa, root velocity) | c_t | root_v ]   (60 + n_c doubles;
+//                  root_v = the filtered, not yet averaged velocity that :159 integrates into the root position)
 //   fb_row[s]    = the (size_s,) float row record_state_aa_and_c appends for the next call.
 constexpr int PP_TAPS = 6, PP_NJ = 18, PP_TAIL = 54;
 
@@ -888,7 +889,7 @@ post_step_kernel(const float* __restrict__ y_last, const float* __restrict__ imu
                  double* __restrict__ ring, double* __restrict__ last_tail, float* __restrict__ fb_row,
                  double* __restrict__ out_state, int size_s, int n_before) {
     const int s = blockIdx.x, lane = threadIdx.x;
-    const int n_c = size_s - 111, out_w = 57 + n_c;
+    const int n_c = size_s - 111, out_w = 60 + n_c;
     double* rg = ring + (size_t)s * PP_TAPS * size_s;
     double* lt = last_tail + (size_t)s * PP_TAIL;
     const float* y = y_last + (size_t)s * size_s;
@@ -961,7 +962,7 @@ post_step_kernel(const float* __restrict__ y_last, const float* __restrict__ imu
         pp_rotmat_to_aa(M, aa);
         st[3 * lane] = aa[0]; st[3 * lane + 1] = aa[1]; st[3 * lane + 2] = aa[2];
     }
-    if (lane >= 29) st[54 + lane - 29] = sm[108 + lane - 29];          // root velocity (:157-158)
+    if (lane >= 29) { st[54 + lane - 29] = sm[108 + lane - 29]; out[57 + n_c + lane - 29] = sm[108 + lane - 29]; }   // root velocity (:154-159)
     __syncwarp();
     // "To make motion a bit smoother": average s_t[6:] with the previous frame's                  (:165-167)
     for (int c = lane; c < PP_TAIL; c += 32) {

@@ -29,6 +29,7 @@ def run_motions(model, imus, s_inits, y_overrides=None):
     Returns a list of dicts, one per motion, with
       ``state`` (T_i, 57)  s_t[3:60] per runner call (rows of the 5 warm-up calls hold s_init[3:60]),
       ``ct``    (T_i, n_c) constraints per call (zeros during warm-up, like the runner),
+      ``root_v``(T_i, 3)   filtered root velocity per call (what :159 integrates into the root position),
       ``valid`` (T_i,)     False for the warm-up calls.
     """
     S = len(imus)
@@ -39,8 +40,9 @@ def run_motions(model, imus, s_inits, y_overrides=None):
     sess = StreamSession(model, n_streams=S)
     sess.set_state(np.stack([np.asarray(s, dtype=np.float64) for s in s_inits]))
     W = sess.state_width
-    n_c = W - 57
-    out = [dict(state=np.zeros((n, 57)), ct=np.zeros((n, n_c)), valid=np.zeros(n, dtype=bool)) for n in lens]
+    n_c = W - 60
+    out = [dict(state=np.zeros((n, 57)), ct=np.zeros((n, n_c)), root_v=np.zeros((n, 3)), valid=np.zeros(n, dtype=bool))
+           for n in lens]
     frame = np.zeros((S, 72), dtype=np.float32)
     for t in range(T):
         for i in range(S):                      # a finished motion keeps replaying its last frame; its output is dropped
@@ -56,6 +58,7 @@ def run_motions(model, imus, s_inits, y_overrides=None):
                 out[i]["state"][t] = np.asarray(s_inits[i], dtype=np.float64)[3:60]
             else:
                 out[i]["state"][t] = st[i, :57]
-                out[i]["ct"][t] = st[i, 57:]
+                out[i]["ct"][t] = st[i, 57:57 + n_c]
+                out[i]["root_v"][t] = st[i, 57 + n_c:]
                 out[i]["valid"][t] = True
     return out

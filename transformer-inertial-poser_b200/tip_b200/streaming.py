@@ -113,7 +113,7 @@ class StreamSession:
 
     def step_closed(self, raw_imu, y_override=None):
         """Push one RAW IMU frame per stream (S, 72) and get the runner's per-frame pose back:
-        (S, W) float64 = [s_t[3:60] | c_t] (see ``tip_stream_step_closed``), or None during the runner's
+        (S, W) float64 = [s_t[3:60] | c_t | root_v] (see ``tip_stream_step_closed``), or None during the runner's
         5 warm-up calls.  The state row is fed back to the model on the device (no per-frame x_s upload).
         ``y_override`` (S, size_s) teacher-forces the post step (parity-test hook)."""
         m = self.model
