@@ -317,6 +317,28 @@ def main():
                       "what": "StreamSession.step with host rows: H2D of one (90,)+(131,) row, window shift, "
                               "forward B=1 L=40, D2H of the last row, stream sync"}
 
+        # the same stream through the closed-loop call (rows N1 + N3): one RAW 72-float IMU row in, the runner's
+        # pose row out; pre-processing, forward, post-model step and state feedback all on the device
+        from scipy.spatial.transform import Rotation
+        sess2 = StreamSession(model, n_streams=1)
+        s0 = np.zeros(114); s0[2] = 0.95
+        sess2.set_state(s0)
+        rs = np.random.RandomState(3)
+        rot = Rotation.random(6, random_state=3)
+        lat2 = []
+        for t in range(700):
+            rot = Rotation.from_rotvec(0.02 * rs.standard_normal((6, 3))) * rot
+            raw = np.concatenate((rot.as_matrix().reshape(54), 3.0 * rs.standard_normal(18))).astype(np.float32)
+            t0 = time.perf_counter()
+            st = sess2.step_closed(raw[None])
+            lat2.append(time.perf_counter() - t0)
+        lat2 = np.array(lat2[100:]) * 1e6
+        stream_lat["closed_loop"] = {"p50_us": float(np.percentile(lat2, 50)), "p99_us": float(np.percentile(lat2, 99)),
+                                     "fps_single_stream": float(1e6 / lat2.mean()), "finite": bool(np.isfinite(st).all()),
+                                     "what": "StreamSession.step_closed: H2D of one raw (72,) IMU row, device IMU pre-processing, "
+                                             "window shift, forward B=1 L=40, device post-model step + state feedback, "
+                                             "D2H of the (80,) float64 pose row, stream sync"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -338,23 +360,36 @@ def main():
     ach_tf = stage_flops.get(dom, 0.0) / (per_launch[dom] * 1e-3) / 1e12
     alg_bytes, alg_flops = model.algorithmic_cost(B, L_WIN)
     fwd_gbs = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp))
+        except Exception:
+            traffic = {}
+    # per-kernel table (per launch): algorithmic TFLOP/s against the measured bf16 peak, share of the forward
+    kernels = {}
+    for k in sorted(totals, key=totals.get, reverse=True):
+        fl = stage_flops.get(k, 0.0)
+        kernels[k] = {"us_per_launch": round(per_launch[k] * 1e3, 2), "launches": launches_per_fwd[k],
+                      "share_of_step": round(totals[k] / tot_stage, 4) if tot_stage else None,
+                      "tflops": round(fl / (per_launch[k] * 1e-3) / 1e12, 2) if fl else None,
+                      "frac_of_bf16_peak": round(fl / (per_launch[k] * 1e-3) / 1e12 / tf_peak, 4) if fl else None,
+                      "dram_bytes_per_launch_ncu": traffic.get(k)}
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": ach_tf, "peak": tf_peak, "unit": "TFLOP/s",
-        "frac": ach_tf / tf_peak, "traffic": None, "peak_kind": f"{peak_kind} bf16 burst (cuBLAS); fp32-parity math is a "
+        "frac": ach_tf / tf_peak, "traffic": traffic.get(dom), "peak_kind": f"{peak_kind} bf16 burst (cuBLAS); fp32-parity math is a "
         "3-product FP16 split (3 MMAs per product), so the reachable ceiling is peak/3",
         "us_per_launch": per_launch[dom] * 1e3, "share_of_step": totals[dom] / tot_stage if tot_stage else None,
+        "stage_timing": "separate pass with a CUDA event before every kernel (graph replay off), L2 flushed; the events add "
+                        "~4 us per kernel, so the stage sum exceeds ms_per_step",
         "stage_us_per_forward": {k: round(v * 1e3, 2) for k, v in sorted(totals.items(), key=lambda kv: -kv[1])},
+        "kernels": kernels,
         "forward_hbm": {"bound": "hbm", "achieved": fwd_gbs, "peak": hbm_peak, "unit": "GB/s",
                         "frac": fwd_gbs / hbm_peak, "algorithmic_bytes": alg_bytes},
         "forward_tensor": {"achieved": alg_flops / (ms_per_step * 1e-3) / 1e12, "peak": tf_peak,
                            "unit": "TFLOP/s", "frac": alg_flops / (ms_per_step * 1e-3) / 1e12 / tf_peak},
     }
-    tp = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
-    if os.path.exists(tp):
-        try:
-            roofline["traffic"] = json.load(open(tp)).get(dom)
-        except Exception:
-            pass
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -371,7 +406,8 @@ def main():
         "config": {"workload": f"batch={B} synthetic IMU windows per GPU, seq_len=40, 6 IMUs, fp32, tf_layers=4 "
                                "nhid=1024 heads=16 (BASELINE configs[1]); replicas only",
                    "l2": "256 MiB memset between timed steps (outside the per-step event pair) + 4 rotating input sets",
-                   "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks",
+                   "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks; each step is one "
+                             "forward, replayed as a CUDA graph (25 kernels, programmatic dependent launch)",
                    "engine": {0: "auto (tcgen05 3xFP16 split)", 1: "ffma", 2: "tcgen05-3xfp16"}[args.engine]},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

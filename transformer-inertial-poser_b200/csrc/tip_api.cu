@@ -463,9 +463,9 @@ static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, fl
         __half* oh = reinterpret_cast<__half*>(out);
         __half* ol = reinterpret_cast<__half*>(out_lo);
         // smaller CTAs (fewer heads each) quantise better over the SMs; the qkv pieces stay >= 64 bytes
-        if (hpb == 8)      attention_mma_kernel<8><<<dim3(B, NH / 8), 256, AttnCfg<8>::SMEM_BYTES, st>>>(qh, ql, oh, ol, L, drop_p, seed);
-        else if (hpb == 2) attention_mma_kernel<2><<<dim3(B, NH / 2), 64, AttnCfg<2>::SMEM_BYTES, st>>>(qh, ql, oh, ol, L, drop_p, seed);
-        else               attention_mma_kernel<4><<<dim3(B, NH / 4), 128, AttnCfg<4>::SMEM_BYTES, st>>>(qh, ql, oh, ol, L, drop_p, seed);
+        if (hpb == 8)      launch_k(attention_mma_kernel<8>, dim3(dim3(B, NH / 8)), dim3(256), AttnCfg<8>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, seed);
+        else if (hpb == 2) launch_k(attention_mma_kernel<2>, dim3(dim3(B, NH / 2)), dim3(64), AttnCfg<2>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, seed);
+        else               launch_k(attention_mma_kernel<4>, dim3(dim3(B, NH / 4)), dim3(128), AttnCfg<4>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, seed);
         m->launches++;
         return;
     }
@@ -496,8 +496,13 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
         if (getenv("TIP_VERBOSE")) fprintf(stderr, "[tip] rnn clusters co-schedulable: %d\n", n);
         m->rnn_clusters = n;
     }
-    static const int rnn_kind = getenv("TIP_RNN") ? atoi(getenv("TIP_RNN")) : 0;   // 1: force the FFMA cluster kernel
-    if (hs_lo && m->maps_ready && rnn_kind != 1 && !m->rnn_stream_fallback) {
+    static const int rnn_kind = getenv("TIP_RNN") ? atoi(getenv("TIP_RNN")) : 0;   // 1: force the FFMA cluster kernel, 2: force the tensor-core one
+    // small batches (one group of <= 8 windows per cluster): the FFMA cluster kernel with W_hh in registers has the
+    // shorter step (2.5 vs 2.8 us: no MMA issue phase) -- measured 98 vs 119 us at B <= 8, 104 vs 122 us at B = 64, forward 416 vs 434 us at B = 96;
+    // from ~100 windows on it becomes FFMA-bound and the tensor-core recurrence wins (588 vs 127 us at B = 256)
+    static const int ffma_max_b = getenv("TIP_RNN_FFMA_MAX_B") ? atoi(getenv("TIP_RNN_FFMA_MAX_B")) : 120;
+    const bool small_b = m->rnn_clusters > 0 && B <= std::min(ffma_max_b, RC_GROUP * m->rnn_clusters) && rnn_kind != 2;
+    if (hs_lo && m->maps_ready && rnn_kind != 1 && !small_b && !m->rnn_stream_fallback) {
         // tensor-core recurrence (tcgen05 engine): clusters of 8 CTAs, RU_N windows each
         if (m->rnn_umma_clusters < 0) {
             cudaFuncSetAttribute(rnn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM_BYTES);
@@ -517,11 +522,11 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
             const __half* wh = reinterpret_cast<const __half*>(m->blob + m->off.whh_hi);
             const __half* wl = reinterpret_cast<const __half*>(m->blob + m->off.whh_lo);
             if (a_tmem)
-                rnn_umma_kernel<true><<<nc * RU_CTAS, RU_THREADS, RU_SMEM_BYTES, st>>>(
+                launch_k(rnn_umma_kernel<true>, dim3(nc * RU_CTAS), dim3(RU_THREADS), RU_SMEM_BYTES, st, 
                     m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
                     m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf, wh, wl);
             else
-                rnn_umma_kernel<false><<<nc * RU_CTAS, RU_THREADS, RU_SMEM_BYTES, st>>>(
+                launch_k(rnn_umma_kernel<false>, dim3(nc * RU_CTAS), dim3(RU_THREADS), RU_SMEM_BYTES, st, 
                     m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
                     m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf, wh, wl);
             m->launches++;
@@ -555,6 +560,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
     const float* W = m->blob;
     const int M = B * L;
     m->last_rows = M;
+    pdl_rows() = M;                           // programmatic dependent launch only pays for small forwards
     int rc = ensure_workspace(m, M);
     if (rc != TIP_OK) return rc;
     const float p_in = drop ? drop->in_dropout : 0.f;
@@ -585,7 +591,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
         float* xo = m->xin;
         float* xl = umma ? lo_xin : nullptr;
-        condition_kernel<<<blocks, 256, 0, st>>>(x_imu, x_s, keep_mask, past_scale, xo, xl, M,
+        launch_k(condition_kernel, dim3(blocks), dim3(256), 0, st, x_imu, x_s, keep_mask, past_scale, xo, xl, M,
                                                  d.n_imu, d.size_s, d.kin_pad, p_in, p_past, seed);
         m->launches++;
     }
@@ -613,7 +619,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
                 gp.resid = gp.resid_lo = nullptr; gp.gamma = gp.beta = nullptr;
                 gp.out = m->gi; gp.out_lo = nullptr; gp.ldc = E;               // fp32 [rows][256]; gi is free until rnn_ih
                 umma_gemm(m->maps, which, layer, M, N, K, gp, false, st, 0, -1, true);
-                resid_ln_kernel<<<(M + 7) / 8, 256, 0, st>>>(m->gi, reinterpret_cast<const __half*>(ep.resid),
+                launch_k(resid_ln_kernel, dim3((M + 7) / 8), dim3(256), 0, st, m->gi, reinterpret_cast<const __half*>(ep.resid),
                                                              reinterpret_cast<const __half*>(ep.resid_lo), ep.gamma, ep.beta,
                                                              reinterpret_cast<__half*>(ep.out), reinterpret_cast<__half*>(ep.out_lo), 0, M);
                 m->launches += 2;
@@ -802,7 +808,7 @@ extern "C" int tip_forward_host(tip_model* m, const float* x_imu_h, const float*
     const size_t out_rows = last_row_only ? (size_t)B : rows;
     const float* dsrc = m->d_y;
     if (last_row_only) {
-        last_row_kernel<<<(B * d.size_s + 255) / 256, 256, 0, st>>>(m->d_y, m->d_xs, B, L, d.size_s);
+        launch_k(last_row_kernel, dim3((B * d.size_s + 255) / 256), dim3(256), 0, st, m->d_y, m->d_xs, B, L, d.size_s);
         m->launches++;
         dsrc = m->d_xs;
     }
@@ -853,24 +859,25 @@ extern "C" int tip_stream_length(const tip_model* m) { return m ? m->stream_len 
 static int stream_step_device(tip_model* m, const tip_dropout* drop, cudaStream_t st, int len_before) {
     const Dims& d = m->d;
     const int S = m->n_streams;
+    pdl_rows() = S * MAXL;
     const float* imu_rows = m->st_rows;
     const float* s_rows = m->st_rows + (size_t)S * d.n_imu;
-    window_push_kernel<<<S, 256, 0, st>>>(m->win_imu, imu_rows, d.n_imu, len_before);
-    window_push_kernel<<<S, 256, 0, st>>>(m->win_s, s_rows, d.size_s, len_before);
+    launch_k(window_push_kernel, dim3(S), dim3(256), 0, st, m->win_imu, imu_rows, d.n_imu, len_before);
+    launch_k(window_push_kernel, dim3(S), dim3(256), 0, st, m->win_s, s_rows, d.size_s, len_before);
     m->launches += 2;
     const int L = std::min(len_before + 1, MAXL);
     const float *xi = m->win_imu, *xs = m->win_s;
     int extra = 2;
     if (L < MAXL) {
         const int64_t ti = (int64_t)S * L * d.n_imu, ts = (int64_t)S * L * d.size_s;
-        window_compact_kernel<<<(unsigned)std::min<int64_t>((ti + 255) / 256, 1184), 256, 0, st>>>(m->win_imu, m->st_ximu, S, L, d.n_imu);
-        window_compact_kernel<<<(unsigned)std::min<int64_t>((ts + 255) / 256, 1184), 256, 0, st>>>(m->win_s, m->st_xs, S, L, d.size_s);
+        launch_k(window_compact_kernel, dim3((unsigned)std::min<int64_t>((ti + 255) / 256, 1184)), dim3(256), 0, st, m->win_imu, m->st_ximu, S, L, d.n_imu);
+        launch_k(window_compact_kernel, dim3((unsigned)std::min<int64_t>((ts + 255) / 256, 1184)), dim3(256), 0, st, m->win_s, m->st_xs, S, L, d.size_s);
         xi = m->st_ximu; xs = m->st_xs;
         extra += 2;
     }
     int rc = tip_forward(m, xi, xs, m->st_y, S, L, nullptr, 1.f, drop, st);   // resets m->launches
     if (rc != TIP_OK) return rc;
-    last_row_kernel<<<(S * d.size_s + 255) / 256, 256, 0, st>>>(m->st_y, m->st_ylast, S, L, d.size_s);
+    launch_k(last_row_kernel, dim3((S * d.size_s + 255) / 256), dim3(256), 0, st, m->st_y, m->st_ylast, S, L, d.size_s);
     m->launches += extra + 1;
     return TIP_OK;
 }
@@ -971,7 +978,7 @@ extern "C" int tip_stream_step_raw(tip_model* m, const float* raw_imu, const flo
         TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_raw, raw_imu, n_r * sizeof(float), cudaMemcpyDeviceToDevice, st));
         TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows + n_i, s_row, n_s * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    imu_push_kernel<<<(unsigned)S, 32, 0, st>>>(m->st_raw, m->raw_ring, m->acc_ring, m->st_rows, d.n_imu, m->n_raw, m->n_rows);
+    launch_k(imu_push_kernel, dim3((unsigned)S), dim3(32), 0, st, m->st_raw, m->raw_ring, m->acc_ring, m->st_rows, d.n_imu, m->n_raw, m->n_rows);
     TIP_CUDA_TRY(m, cudaGetLastError());
     m->n_raw += (m->n_raw == 0) ? IMU_DELAY + 1 : 1;
     if (m->n_raw < IMU_RING) {
@@ -1027,7 +1034,7 @@ extern "C" int tip_stream_step_closed(tip_model* m, const float* raw_imu, const 
     }
     // the x_s row of this call is the one the previous post step produced (or the initial state)
     TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows + n_i, m->fb_s, n_s * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    imu_push_kernel<<<(unsigned)S, 32, 0, st>>>(m->st_raw, m->raw_ring, m->acc_ring, m->st_rows, d.n_imu, m->n_raw, m->n_rows);
+    launch_k(imu_push_kernel, dim3((unsigned)S), dim3(32), 0, st, m->st_raw, m->raw_ring, m->acc_ring, m->st_rows, d.n_imu, m->n_raw, m->n_rows);
     TIP_CUDA_TRY(m, cudaGetLastError());
     m->n_raw += (m->n_raw == 0) ? IMU_DELAY + 1 : 1;
     if (m->n_raw < IMU_RING) {
@@ -1045,7 +1052,7 @@ extern "C" int tip_stream_step_closed(tip_model* m, const float* raw_imu, const 
                                         rows_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
         ysrc = m->st_y;
     }
-    post_step_kernel<<<(unsigned)S, 32, 0, st>>>(ysrc, m->st_rows, d.n_imu, m->pp_ring, m->pp_last, m->fb_s, m->pp_out,
+    launch_k(post_step_kernel, dim3((unsigned)S), dim3(32), 0, st, ysrc, m->st_rows, d.n_imu, m->pp_ring, m->pp_last, m->fb_s, m->pp_out,
                                                  d.size_s, m->n_post);
     TIP_CUDA_TRY(m, cudaGetLastError());
     m->launches += 2;                       // imu_push + post_step

@@ -51,6 +51,8 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
     constexpr int AM_ROWB = AttnCfg<AM_HPB>::ROWB, AM_QK_BYTES = AttnCfg<AM_HPB>::QK_BYTES, AM_V_BYTES = AttnCfg<AM_HPB>::V_BYTES;
     constexpr int CPR = AM_HPB * 2;                  // 16-byte chunks per row of a plane tile
     extern __shared__ __align__(16) uint8_t am_smem[];
+    griddep_wait();
+    griddep_launch();
     uint8_t* sKh = am_smem;                          // [L][8 heads][16] halves
     uint8_t* sKl = sKh + AM_QK_BYTES;
     uint8_t* sVh = sKl + AM_QK_BYTES;                // [48 keys][8 heads][16] halves, rows >= L zero

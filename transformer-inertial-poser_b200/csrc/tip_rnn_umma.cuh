@@ -126,6 +126,8 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
     }
     cluster_arrive();          // every CTA's barriers are initialised before any peer pushes into it
     cluster_wait();
+    griddep_wait();            // PDL: the W_hh slice (a weight) was requested above, while rnn_ih was still running
+    griddep_launch();
 
     uint32_t hpar0 = 0, hpar1 = 0; // phase parities of h_full[0/1] (MMA issuer)
     uint32_t apar = 0;             // phase parity of acc_full (epilogue threads)

@@ -38,6 +38,8 @@ __global__ void condition_kernel(const float* __restrict__ x_imu, const float* _
                                  float* __restrict__ out, float* __restrict__ out_lo,
                                  int M, int n_imu, int size_s, int kin_pad,
                                  float p_in, float p_past, uint64_t seed) {
+    griddep_wait();
+    griddep_launch();
     const int groups = kin_pad >> 3;
     const int64_t total = (int64_t)M * groups;
     const float inv_in = p_in > 0.f ? 1.f / (1.f - p_in) : 1.f;
@@ -663,6 +665,8 @@ rnn_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh,
 // earlier -- coalesced both ways), then append the new row.  One CTA per stream and window.
 __global__ void __launch_bounds__(256)
 window_push_kernel(float* __restrict__ win, const float* __restrict__ new_row, int width, int len) {
+    griddep_wait();
+    griddep_launch();
     // win: (S, MAXL, width); len = rows currently held (same for every stream)
     float* w = win + (size_t)blockIdx.x * MAXL * width;
     const float* nr = new_row + (size_t)blockIdx.x * width;
@@ -703,6 +707,8 @@ constexpr int IMU_RAW = 72, IMU_RING = 11, IMU_DELAY = 5, ACC_WIN = 40;
 __global__ void __launch_bounds__(32)
 imu_push_kernel(const float* __restrict__ raw_new, float* __restrict__ raw_ring, double* __restrict__ acc_ring,
                 float* __restrict__ row_out, int n_imu, int n_raw_before, int n_rows_before) {
+    griddep_wait();
+    griddep_launch();
     const int s = blockIdx.x, lane = threadIdx.x;
     float* ring = raw_ring + (size_t)s * IMU_RING * IMU_RAW;
     double* aring = acc_ring + (size_t)s * ACC_WIN * 18;
@@ -771,6 +777,8 @@ __global__ void __launch_bounds__(256)
 resid_ln_kernel(const float* __restrict__ pre, const __half* __restrict__ res_hi, const __half* __restrict__ res_lo,
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 __half* __restrict__ out_hi, __half* __restrict__ out_lo, int row0, int rows) {
+    griddep_wait();
+    griddep_launch();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + warp;
     if (r >= rows) return;
@@ -888,6 +896,8 @@ __global__ void __launch_bounds__(32)
 post_step_kernel(const float* __restrict__ y_last, const float* __restrict__ imu_rows, int n_imu,
                  double* __restrict__ ring, double* __restrict__ last_tail, float* __restrict__ fb_row,
                  double* __restrict__ out_state, int size_s, int n_before) {
+    griddep_wait();
+    griddep_launch();
     const int s = blockIdx.x, lane = threadIdx.x;
     const int n_c = size_s - 111, out_w = 60 + n_c;
     double* rg = ring + (size_t)s * PP_TAPS * size_s;
@@ -986,6 +996,8 @@ post_step_kernel(const float* __restrict__ y_last, const float* __restrict__ imu
 // gather compacted (S, L, width) windows out of the (S, MAXL, width) storage when L < MAXL
 __global__ void window_compact_kernel(const float* __restrict__ win, float* __restrict__ out,
                                       int S, int L, int width) {
+    griddep_wait();
+    griddep_launch();
     const int64_t total = (int64_t)S * L * width;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -998,6 +1010,8 @@ __global__ void window_compact_kernel(const float* __restrict__ win, float* __re
 // y_last[b, :] = y[b, L-1, :]
 __global__ void last_row_kernel(const float* __restrict__ y, float* __restrict__ y_last,
                                 int B, int L, int size_s) {
+    griddep_wait();
+    griddep_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B * size_s) {
         const int b = i / size_s, c = i - b * size_s;

@@ -298,6 +298,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     if constexpr (CG == 2) { cluster_arrive(); cluster_wait(); }   // the peer's barriers exist before anything signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();          // PDL: everything above overlapped the previous kernel; its results are needed from here on
+    griddep_launch();
 #define TIP_TS(i) do { if (ep.tbuf && blockIdx.x == 0 && lane == 0) ep.tbuf[i] = ptx::globaltimer_ns(); } while (0)
     if (warp == 2) TIP_TS(0);
 
@@ -969,14 +971,12 @@ inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, c
         const UmmaOperand* B64 = (which == UG_OUT) ? &mp.w_o64[layer] : &mp.w_264[layer];
         ep.tma_out = (mp.o_pre.valid && !getenv("TIP_NO_TMA_STORE")) ? 1 : 0;
         const int tiles = m_tiles * (N / 64);
-        umma_gemm_kernel<64, false, false><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<64>::SMEM_BYTES, st>>>(
-            A->hi, A->lo, B64->hi, B64->lo, mp.o_pre.c0, mp.o_pre.c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+        launch_k(umma_gemm_kernel<64, false, false>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<64>::SMEM_BYTES, st, A->hi, A->lo, B64->hi, B64->lo, mp.o_pre.c0, mp.o_pre.c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
         return;
     }
     if (ln) {
         const int tiles = m_tiles;                                // BN = 256 = the whole row
-        umma_gemm_kernel<256, true, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<256>::SMEM_BYTES, st>>>(
-            A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+        launch_k(umma_gemm_kernel<256, true, true>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<256>::SMEM_BYTES, st, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
     } else if (B256 && (N % 256) == 0 && (m_tiles % 2) == 0 && (m_tiles / 2) * (N / 256) >= 32 && pair_mode()) {
         // CTA pairs (cta_group::2): 256 x 256 tiles, each CTA stages its 128 rows of A and half of B
         const int units = (m_tiles / 2) * (N / 256);
@@ -985,10 +985,12 @@ inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, c
         cfg.blockDim = dim3(UM_THREADS);
         cfg.dynamicSmemBytes = UmmaCfg<256, 2>::SMEM_BYTES;
         cfg.stream = st;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
         if (ep.out_lo)
             cudaLaunchKernelEx(&cfg, umma_gemm_kernel<256, false, true, 2>, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
         else
@@ -997,19 +999,15 @@ inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, c
         // wide tiles: A is re-used over 256 columns (25 % less L2->SM operand traffic per flop)
         const int tiles = m_tiles * (N / 256);
         if (ep.out_lo)
-            umma_gemm_kernel<256, false, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<256>::SMEM_BYTES, st>>>(
-                A->hi, A->lo, B256->hi, B256->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+            launch_k(umma_gemm_kernel<256, false, true>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<256>::SMEM_BYTES, st, A->hi, A->lo, B256->hi, B256->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
         else
-            umma_gemm_kernel<256, false, false><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<256>::SMEM_BYTES, st>>>(
-                A->hi, A->lo, B256->hi, B256->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+            launch_k(umma_gemm_kernel<256, false, false>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<256>::SMEM_BYTES, st, A->hi, A->lo, B256->hi, B256->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
     } else {
         const int tiles = m_tiles * ((N + 127) / 128);
         if (ep.out_lo)
-            umma_gemm_kernel<128, false, true><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<128>::SMEM_BYTES, st>>>(
-                A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+            launch_k(umma_gemm_kernel<128, false, true>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<128>::SMEM_BYTES, st, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
         else
-            umma_gemm_kernel<128, false, false><<<std::min(tiles, mp.num_sms), UM_THREADS, UmmaCfg<128>::SMEM_BYTES, st>>>(
-                A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+            launch_k(umma_gemm_kernel<128, false, false>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<128>::SMEM_BYTES, st, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
     }
 }
 
