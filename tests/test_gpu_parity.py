@@ -290,3 +290,38 @@ def test_raw_imu_preprocessing_on_device():
             assert np.abs(y - ref).max() < TOL, (t, np.abs(y - ref).max())
         n_out += 1
     assert n_out == T - 5 and sess.length == 40
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_batch_sizes_across_kernel_switch_points(engine):
+    """L = 40 at batch sizes on both sides of every dispatch threshold: skinny LayerNorm path (<= 8 row tiles,
+    B <= 25), small-batch recurrence with 1 / 2 / 4 / 8 windows per cluster, FFMA cluster recurrence, tensor-core
+    recurrence (> ~120 windows), programmatic dependent launch (<= 1024 rows)."""
+    sd = O.random_state_dict(23)
+    m = make_model(sd, engine=engine)
+    for seed, B in enumerate([1, 2, 9, 16, 17, 25, 26, 31, 61, 100, 121, 140]):
+        x_imu, x_s = O.synth_inputs(300 + seed, B, 40, nan_frac=0.1)
+        y = run(m, x_imu, x_s)
+        ref = O.forward(sd, x_imu, x_s)
+        err = np.abs(y - ref).max()
+        assert np.isfinite(y).all() and err < TOL, (B, err)
+
+
+def test_graph_replay_reads_fresh_data():
+    """A forward on the same buffers is replayed from a CUDA graph from the third call on; the replay must see the
+    buffers' current contents, and switching graphs off must give the same numbers."""
+    sd = O.random_state_dict(24)
+    m = make_model(sd)
+    for B in (1, 40):
+        xi = torch.empty((B, 40, 90), device="cuda")
+        xs = torch.empty((B, 40, 131), device="cuda")
+        for it in range(5):
+            a, b = O.synth_inputs(400 + it, B, 40)
+            xi.copy_(torch.from_numpy(a)); xs.copy_(torch.from_numpy(b))
+            y = m(xi, xs).cpu().numpy()
+            ref = O.forward(sd, a, b)
+            assert np.abs(y - ref).max() < TOL, (B, it)
+        m.set_use_graphs(False)
+        y2 = m(xi, xs).cpu().numpy()
+        m.set_use_graphs(True)
+        np.testing.assert_array_equal(y, y2)

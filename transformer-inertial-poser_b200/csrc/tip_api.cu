@@ -533,6 +533,16 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
             return;
         }
     }
+    static const int small_on = getenv("TIP_RNN_SMALL") ? atoi(getenv("TIP_RNN_SMALL")) : 1;
+    if (small_on && m->rnn_clusters > 0 && !m->rnn_stream_fallback && B <= m->rnn_clusters && rnn_kind != 1) {
+        // one window per cluster: latency-optimised kernel (st.async exchange straight from registers).  Measured:
+        // recurrence 98 -> 76 us, B = 1 forward 293 -> 264 us.  With 2+ windows per cluster its serial tail (16 lanes
+        // doing tanh + 8 remote stores per window) loses to the group kernel below (B = 16: 127 vs 104 us), so it is
+        // only used while every window gets its own cluster.
+        launch_k(rnn_small_kernel<1>, dim3(B * RC_CTAS), dim3(256), 0, st, gi, m->blob + m->off.whh, hs, hs_lo, B, L, g_rnn_tbuf);
+        m->launches++;
+        return;
+    }
     if (m->rnn_clusters > 0 && !m->rnn_stream_fallback) {
         // windows per cluster pass: spread the batch over all co-resident clusters, in whole groups of 8
         const int ncl = m->rnn_clusters;

@@ -659,6 +659,126 @@ rnn_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small-batch recurrence (streaming: a handful of windows).  Same decomposition as rnn_cluster_kernel -- a cluster
+// of 8 CTAs, W_hh in registers (thread = 4 hidden units x one 32-wide k-slice) -- but built for the latency of ONE
+// step, which is all that matters when NW <= 8 windows share a cluster:
+//   * every CTA keeps the FULL h vector of its NW windows in shared memory (double-buffered over the step parity);
+//   * the 16 lanes that finish 4 units each send them straight from registers to all 8 CTAs with
+//     st.async.shared::cluster (16 bytes per store, bytes counted on the destination's mbarrier): no staging tile,
+//     no proxy fence, no CTA barrier and no bulk-copy engine between tanh and the peers' next step.
+template <int NW>
+__global__ void __cluster_dims__(RC_CTAS, 1, 1) __launch_bounds__(256, 1)
+rnn_small_kernel(const float* __restrict__ gi, const float* __restrict__ whh,
+                 float* __restrict__ hs, float* __restrict__ hs_lo, int B, int L, unsigned long long* tbuf) {
+    __shared__ __align__(16) float hbuf[2][NW][R];
+    __shared__ __align__(8) uint64_t full_bar[2];
+    const int tid = threadIdx.x;
+    const int ug = tid >> 4, s = tid & 15;
+    const uint32_t rank = cluster_ctarank();
+    const int unit0 = (int)rank * RC_UNITS + ug * 4;
+    const int n_clusters = gridDim.x / RC_CTAS, cluster_id = blockIdx.x / RC_CTAS;
+    float w[4][32];                                          // W_hh[unit0 + u][32 s + kk] (weights: before the PDL wait)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float4* wp = reinterpret_cast<const float4*>(whh + (size_t)(unit0 + u) * R + s * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t4 = __ldg(wp + j);
+            w[u][4 * j] = t4.x; w[u][4 * j + 1] = t4.y; w[u][4 * j + 2] = t4.z; w[u][4 * j + 3] = t4.w;
+        }
+    }
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&full_bar[0]);
+    const uint32_t hbuf_s = (uint32_t)__cvta_generic_to_shared(&hbuf[0][0][0]);
+    if (tid == 0) {
+        rc_mbar_init(bar_s, 1);
+        rc_mbar_init(bar_s + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_arrive();
+    cluster_wait();
+    griddep_wait();
+    griddep_launch();
+    uint32_t par0 = 0, par1 = 0;
+    for (int b0 = cluster_id * NW; b0 < B; b0 += n_clusters * NW) {
+        for (int t = 0; t < L; ++t) {
+            const int cur = t & 1, nxt = cur ^ 1;
+            // this step's h_t lands in buffer nxt of every CTA: 512 floats per window from the 8 CTAs (self included)
+            if (tid == 0 && t + 1 < L) rc_mbar_expect(bar_s + 8u * nxt, (uint32_t)(NW * R * sizeof(float)));
+            float4 g4[NW];
+            if (s == 0) {
+#pragma unroll
+                for (int wi = 0; wi < NW; ++wi)
+                    g4[wi] = __ldg(reinterpret_cast<const float4*>(gi + ((size_t)min(b0 + wi, B - 1) * L + t) * R + unit0));
+            }
+            float acc[NW][4];
+#pragma unroll
+            for (int wi = 0; wi < NW; ++wi) acc[wi][0] = acc[wi][1] = acc[wi][2] = acc[wi][3] = 0.f;
+            if (t > 0) {
+                if (cur) { rc_mbar_wait(bar_s + 8u, par1); par1 ^= 1u; }
+                else     { rc_mbar_wait(bar_s, par0); par0 ^= 1u; }
+                if (tbuf && blockIdx.x == 0 && tid == 0 && (t == 20 || t == 21)) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tbuf[(t - 20) * 4]));
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc) {
+#pragma unroll
+                    for (int wi = 0; wi < NW; ++wi) {
+                        const float4 hv = *reinterpret_cast<const float4*>(&hbuf[cur][wi][32 * s + 4 * kc]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float a = acc[wi][u];
+                            a = fmaf(w[u][4 * kc], hv.x, a);
+                            a = fmaf(w[u][4 * kc + 1], hv.y, a);
+                            a = fmaf(w[u][4 * kc + 2], hv.z, a);
+                            a = fmaf(w[u][4 * kc + 3], hv.w, a);
+                            acc[wi][u] = a;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {                 // sum over the 16 k-slices (lanes of a half warp)
+#pragma unroll
+                    for (int wi = 0; wi < NW; ++wi)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) acc[wi][u] += __shfl_xor_sync(0xffffffffu, acc[wi][u], o);
+                }
+            }
+            if (tbuf && blockIdx.x == 0 && tid == 0 && t == 20) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tbuf[1]));
+            if (s == 0) {
+#pragma unroll
+                for (int wi = 0; wi < NW; ++wi) {
+                    float4 h4;
+                    h4.x = tanhf(acc[wi][0] + g4[wi].x); h4.y = tanhf(acc[wi][1] + g4[wi].y);
+                    h4.z = tanhf(acc[wi][2] + g4[wi].z); h4.w = tanhf(acc[wi][3] + g4[wi].w);
+                    if (t + 1 < L) {
+                        const uint32_t dst = hbuf_s + (uint32_t)(((nxt * NW + wi) * R + unit0) * sizeof(float));
+#pragma unroll
+                        for (uint32_t c = 0; c < RC_CTAS; ++c) {
+                            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                                         ::"r"(map_to_cta(dst, c)), "r"(__float_as_uint(h4.x)), "r"(__float_as_uint(h4.y)),
+                                           "r"(__float_as_uint(h4.z)), "r"(__float_as_uint(h4.w)),
+                                           "r"(map_to_cta(bar_s + 8u * nxt, c)) : "memory");
+                        }
+                    }
+                    if (b0 + wi < B) {
+                        const size_t o = ((size_t)(b0 + wi) * L + t) * R + unit0;
+                        if (hs_lo) {
+                            half_split_store4(reinterpret_cast<__half*>(hs) + o, reinterpret_cast<__half*>(hs_lo) + o,
+                                              make_float4(h4.x * ACT_SCALE, h4.y * ACT_SCALE, h4.z * ACT_SCALE, h4.w * ACT_SCALE));
+                        } else {
+                            *reinterpret_cast<float4*>(hs + o) = h4;
+                        }
+                    }
+                }
+            }
+            if (tbuf && blockIdx.x == 0 && tid == 0 && t == 20) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tbuf[2]));
+        }
+        // the next block of windows restarts at parity 0 with fresh barriers' phases in step; make sure every CTA has
+        // consumed its last buffer before anyone overwrites it
+        cluster_arrive();
+        cluster_wait();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Per-frame window update of the streaming path (replaces the runner's per-frame re-assembly,
 // real_time_runner_minimal.py:131-147): when a stream's window is full, slide it up by one row
 // (in place: every thread first reads its elements, the CTA synchronises, then writes them one row
