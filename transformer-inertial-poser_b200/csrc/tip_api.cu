@@ -507,6 +507,7 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
         if (m->rnn_umma_clusters < 0) {
             cudaFuncSetAttribute(rnn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM_BYTES);
             cudaFuncSetAttribute(rnn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM_BYTES);
+            cudaFuncSetAttribute(rnn_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM_BYTES);
             cudaLaunchConfig_t q{};
             q.gridDim = dim3(RU_CTAS * 18); q.blockDim = dim3(RU_THREADS); q.dynamicSmemBytes = RU_SMEM_BYTES;
             int n = 0;
@@ -521,12 +522,17 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
             static const int a_tmem = getenv("TIP_RNN_TMEMA") ? atoi(getenv("TIP_RNN_TMEMA")) : 0;
             const __half* wh = reinterpret_cast<const __half*>(m->blob + m->off.whh_hi);
             const __half* wl = reinterpret_cast<const __half*>(m->blob + m->off.whh_lo);
+            static const int st_async = getenv("TIP_RNN_STASYNC") ? atoi(getenv("TIP_RNN_STASYNC")) : 0;
             if (a_tmem)
-                launch_k(rnn_umma_kernel<true>, dim3(nc * RU_CTAS), dim3(RU_THREADS), RU_SMEM_BYTES, st, 
+                launch_k(rnn_umma_kernel<true>, dim3(nc * RU_CTAS), dim3(RU_THREADS), RU_SMEM_BYTES, st,
+                    m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
+                    m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf, wh, wl);
+            else if (st_async)
+                launch_k(rnn_umma_kernel<false, true>, dim3(nc * RU_CTAS), dim3(RU_THREADS), RU_SMEM_BYTES, st,
                     m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
                     m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf, wh, wl);
             else
-                launch_k(rnn_umma_kernel<false>, dim3(nc * RU_CTAS), dim3(RU_THREADS), RU_SMEM_BYTES, st, 
+                launch_k(rnn_umma_kernel<false>, dim3(nc * RU_CTAS), dim3(RU_THREADS), RU_SMEM_BYTES, st,
                     m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
                     m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf, wh, wl);
             m->launches++;

@@ -47,7 +47,9 @@ constexpr int RU_TMEM_COLS = 64 * RU_NACC;
 constexpr int RU_TMEM_COLS_A = 512;
 constexpr int RU_A_COL0 = 64 * RU_NACC;              // first TMEM column of the A operand (the accumulators come first)
 
-template <bool A_TMEM>
+// ST_ASYNC: the 6 KB tile goes to the 7 peers as 16-byte st.async stores issued by all epilogue threads (bytes counted
+// on the destination's mbarrier like the bulk copies) instead of 7 cp.async.bulk pushes issued by 7 threads.
+template <bool A_TMEM, bool ST_ASYNC = false>
 __global__ void __cluster_dims__(RU_CTAS, 1, 1) __launch_bounds__(RU_THREADS, 1)
 rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
                 const float* __restrict__ gi, __half* __restrict__ hs_hi, __half* __restrict__ hs_lo,
@@ -247,7 +249,20 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
                 if (t + 1 < L) {
                     // publish: local arrival + the 7 peers' bytes complete h_full[nxt] in every CTA
                     if (et == 32) ptx::mbar_expect_tx(&h_full[nxt], RU_PUSH_BYTES);
-                    if (et < RU_CTAS && (uint32_t)et != rank) {
+                    if constexpr (ST_ASYNC) {
+                        const uint32_t src = ptx::smem_u32(tile);
+                        const uint32_t bar = ptx::smem_u32(&h_full[nxt]);
+                        for (int i = et; i < RU_B_KB_BYTES / 16; i += 32 * RU_EPI_WARPS) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(tile + i * 16);
+#pragma unroll
+                            for (uint32_t c = 1; c < RU_CTAS; ++c) {
+                                const uint32_t dstc = (rank + c) & (RU_CTAS - 1);
+                                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                                             ::"r"(map_to_cta(src + i * 16, dstc)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+                                               "r"(map_to_cta(bar, dstc)) : "memory");
+                            }
+                        }
+                    } else if (et < RU_CTAS && (uint32_t)et != rank) {
                         const uint32_t src = ptx::smem_u32(tile);
                         dsmem_bulk_push(map_to_cta(src, (uint32_t)et), src, RU_B_KB_BYTES,
                                         map_to_cta(ptx::smem_u32(&h_full[nxt]), (uint32_t)et));

@@ -677,13 +677,15 @@ rnn_small_kernel(const float* __restrict__ gi, const float* __restrict__ whh,
     const uint32_t rank = cluster_ctarank();
     const int unit0 = (int)rank * RC_UNITS + ug * 4;
     const int n_clusters = gridDim.x / RC_CTAS, cluster_id = blockIdx.x / RC_CTAS;
-    float w[4][32];                                          // W_hh[unit0 + u][32 s + kk] (weights: before the PDL wait)
+    // k-slice s = the float4 chunks 16 j + s, j = 0..7 (interleaved, so that the 16 lanes of a half warp read 16
+    // CONSECUTIVE float4 of h: conflict-free; contiguous 32-float slices would make every load a 16-way conflict)
+    float w[4][32];                                          // W_hh[unit0 + u][4 (16 j + s) + e]  (weights: before the PDL wait)
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const float4* wp = reinterpret_cast<const float4*>(whh + (size_t)(unit0 + u) * R + s * 32);
+        const float4* wp = reinterpret_cast<const float4*>(whh + (size_t)(unit0 + u) * R) + s;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 t4 = __ldg(wp + j);
+            const float4 t4 = __ldg(wp + 16 * j);
             w[u][4 * j] = t4.x; w[u][4 * j + 1] = t4.y; w[u][4 * j + 2] = t4.z; w[u][4 * j + 3] = t4.w;
         }
     }
@@ -721,7 +723,7 @@ rnn_small_kernel(const float* __restrict__ gi, const float* __restrict__ whh,
                 for (int kc = 0; kc < 8; ++kc) {
 #pragma unroll
                     for (int wi = 0; wi < NW; ++wi) {
-                        const float4 hv = *reinterpret_cast<const float4*>(&hbuf[cur][wi][32 * s + 4 * kc]);
+                        const float4 hv = *reinterpret_cast<const float4*>(&hbuf[cur][wi][4 * (16 * kc + s)]);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             float a = acc[wi][u];
