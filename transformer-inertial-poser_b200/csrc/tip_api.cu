@@ -619,6 +619,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
             ep.acc_scale = W + o.scales + sc;
             static const int dbg = getenv("TIP_DBG") ? atoi(getenv("TIP_DBG")) : 0;
             ep.dbg = dbg;
+            ep.pdl_early = (M <= 1024) ? 1 : 0;
             ep.tbuf = nullptr;
             static const int ts_on = getenv("TIP_TS") ? atoi(getenv("TIP_TS")) : 0;
             if ((dbg & 4) || ts_on) {

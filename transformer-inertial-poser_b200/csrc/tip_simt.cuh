@@ -84,6 +84,7 @@ struct Epi {
     int dbg;                // experiment flags (TIP_DBG env): 1 skip stores, 2 skip bias loads
     unsigned long long* tbuf;   // optional phase timestamps of CTA 0 (TIP_DBG & 4)
     int tma_out;            // tcgen05 engine: the output goes through TMA store boxes
+    int pdl_early;          // programmatic dependent launch: trigger the next kernel at the start (small forwards) or at the end
 };
 
 constexpr int SG_BK = 16;

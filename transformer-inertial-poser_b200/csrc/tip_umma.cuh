@@ -253,6 +253,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                  const __grid_constant__ CUtensorMap mapC0, const __grid_constant__ CUtensorMap mapC1,
                  const __grid_constant__ CUtensorMap mapR_hi, const __grid_constant__ CUtensorMap mapR_lo,
                  int M, int N, int K, int m_tile0, int m_tile_cnt, Epi ep) {
+    const bool pdl_early = ep.pdl_early != 0;
     using Cfg = UmmaCfg<BN, CG>;
     constexpr int STAGES = Cfg::STAGES;
     static_assert(CG == 1 || (CG == 2 && !LN && BN == 256), "pair tiles: 256 x 256, no LayerNorm epilogue");
@@ -299,7 +300,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     griddep_wait();          // PDL: everything above overlapped the previous kernel; its results are needed from here on
-    griddep_launch();
+    if (pdl_early) griddep_launch();
 #define TIP_TS(i) do { if (ep.tbuf && blockIdx.x == 0 && lane == 0) ep.tbuf[i] = ptx::globaltimer_ns(); } while (0)
     if (warp == 2) TIP_TS(0);
 
@@ -793,6 +794,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
             }
         }
     }
+    if (!pdl_early) griddep_launch();                              // late trigger: the next kernel's launch + prologue overlap only this tail
     if (warp >= 2 && lane == 0) ptx::bulk_wait0();                 // outstanding TMA stores of this warp
     ptx::tc_fence_before();
     __syncthreads();
