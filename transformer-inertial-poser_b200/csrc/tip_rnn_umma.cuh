@@ -28,18 +28,19 @@ constexpr int RU_CTAS = 8;
 constexpr int RU_UNITS = R / RU_CTAS;                 // 64 hidden units per CTA (128 stacked A rows)
 constexpr int RU_N = 24;                              // windows per cluster pass (48 stacked B rows)
 constexpr int RU_EPI_WARPS = 8;
-constexpr int RU_THREADS = 32 + 32 * RU_EPI_WARPS;    // warp 0: MMA issuer / TMEM owner; warps 1..8: epilogue
+constexpr int RU_THREADS = 64 + 32 * RU_EPI_WARPS;    // warp 0: MMA issuer / TMEM owner; warps 1..8: epilogue; warp 9: second MMA issuer
 constexpr int RU_A_KB_BYTES = 2 * RU_UNITS * 128;     // 16 KB: one k-block (64 k) of the stacked W_hh slice
 constexpr int RU_A_BYTES = 8 * RU_A_KB_BYTES;         // 128 KB
 constexpr int RU_B_KB_BYTES = 2 * RU_N * 128;         // 6 KB: one k-block of stacked h (hi rows, then lo rows)
 constexpr int RU_B_BYTES = 8 * RU_B_KB_BYTES;         // 48 KB per parity
 constexpr int RU_SMEM_BYTES = RU_A_BYTES + 2 * RU_B_BYTES + 256;
 constexpr uint32_t RU_PUSH_BYTES = (RU_CTAS - 1) * RU_B_KB_BYTES;         // what the 7 peers deliver per step
-// RU_NACC independent accumulators (k-block kb -> accumulator kb % RU_NACC, 64 TMEM columns apart; the epilogue adds
-// the partial sums).  Experiment: with 4 accumulators the 32 MMAs of a step no longer form one dependent chain, yet
-// the issue phase stays 1.0 us (31 ns per M=128 x N=48 x K=16 MMA) -- like the A-in-TMEM variant this shows that the
-// single issuing thread, not the accumulate dependency or the shared-memory operand read, paces these small MMAs.
-constexpr int RU_NACC = 1;
+// ISS issuing threads (template parameter of the kernel): with ISS = 2 a second warp issues the MMAs of k-blocks 4..7
+// into a second accumulator (64 TMEM columns further) while warp 0 issues k-blocks 0..3; each commits on acc_full
+// (count ISS) and the epilogue adds the partial sums.  (An earlier experiment with 4 accumulators fed by ONE thread
+// left the issue phase at 1.0 us -- 31 ns per M=128 x N=48 x K=16 MMA -- and so did the A-in-TMEM variant: the
+// single issuing thread paces these small MMAs, not the accumulate dependency or the operand read.)
+constexpr int RU_NACC = 2;                           // accumulators allocated
 constexpr int RU_TMEM_COLS = 64 * RU_NACC;
 // A_TMEM variant: the W_hh slice lives in TENSOR MEMORY instead of shared memory (128 lanes x 256 32-bit
 // columns = 128 stacked rows x 512 fp16 k), so each MMA reads only the small h operand from shared memory;
@@ -49,7 +50,10 @@ constexpr int RU_A_COL0 = 64 * RU_NACC;              // first TMEM column of the
 
 // ST_ASYNC: the 6 KB tile goes to the 7 peers as 16-byte st.async stores issued by all epilogue threads (bytes counted
 // on the destination's mbarrier like the bulk copies) instead of 7 cp.async.bulk pushes issued by 7 threads.
-template <bool A_TMEM, bool ST_ASYNC = false>
+// PIPE: one mbarrier per (parity, source CTA) instead of one per parity; every CTA pushes its tile to the peers in ring
+// order (rank+1 first) from ONE thread, so the tiles reach a CTA staggered in time (rank-1's first), and the issuer
+// consumes the k-blocks in that order: the MMAs of a step overlap the DSMEM all-gather instead of following it.
+template <bool A_TMEM, bool ST_ASYNC = false, int ISS = 1, bool PIPE = false>
 __global__ void __cluster_dims__(RU_CTAS, 1, 1) __launch_bounds__(RU_THREADS, 1)
 rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
                 const float* __restrict__ gi, __half* __restrict__ hs_hi, __half* __restrict__ hs_lo,
@@ -64,6 +68,8 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
     uint64_t* h_full = bars + 1;                           // [2] h_t complete in a parity buffer (local arrive + 7 pushes)
     uint64_t* acc_full = bars + 3;                         // MMAs of the step retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint64_t* hk_full = bars + 8;                          // PIPE: [2 parities][8 source CTAs]
+    static_assert(!PIPE || (!ST_ASYNC && ISS == 1), "PIPE builds on the bulk-copy, single-issuer kernel");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -75,7 +81,8 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
         ptx::mbar_init(w_full, 1);
         ptx::mbar_init(&h_full[0], 1);
         ptx::mbar_init(&h_full[1], 1);
-        ptx::mbar_init(acc_full, 1);
+        ptx::mbar_init(acc_full, ISS);
+        if constexpr (PIPE) for (int i = 0; i < 2 * RU_CTAS; ++i) ptx::mbar_init(&hk_full[i], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 0) ptx::tmem_alloc(tmem_slot, A_TMEM ? RU_TMEM_COLS_A : RU_TMEM_COLS);
@@ -86,7 +93,7 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
     if constexpr (A_TMEM) {
         // resident A operand in tensor memory: TMEM lane 32q + l holds stacked row (q, l) = [hi rows of units
         // 16q..16q+15 | lo rows of the same units]; 32-bit column c holds k = 2c, 2c+1 (K-major, packed pairs)
-        if (warp >= 1) {
+        if (warp >= 1 && warp <= RU_EPI_WARPS) {
             const int q = warp & 3, ch = (warp - 1) >> 2;
             const int unit = (int)rank * RU_UNITS + q * 16 + (lane & 15);
             const __half* src = ((lane >> 4) ? whh_lo : whh_hi) + (size_t)unit * R + ch * 256;
@@ -136,42 +143,55 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
 
     for (int rb = cluster_id; rb * RU_N < B; rb += n_clusters) {
         const int b0 = rb * RU_N;
-        if (warp == 0) {
-            // ================= MMA issuer =================
-            if (lane == 0) {
+        if (warp == 0 || warp == 1 + RU_EPI_WARPS) {
+            // ================= MMA issuer(s): warp 0 -> k-blocks [0, 8 / ISS), warp 9 -> the rest =================
+            const int iss = (warp == 0) ? 0 : 1;
+            if (lane == 0 && iss < ISS) {
                 constexpr uint32_t idesc = umma_idesc_f16(2 * RU_UNITS, 2 * RU_N);
                 if constexpr (!A_TMEM) ptx::mbar_wait(w_full, 0);   // completes once; later waits return immediately
                 const uint32_t a0 = ptx::smem_u32(sA);
+                const uint32_t d_acc = tmem_base + (uint32_t)(iss * 64);
+                const int kb0 = iss * (8 / ISS), kb1 = kb0 + 8 / ISS;
                 for (int t = 1; t < L; ++t) {              // step 0 has h = 0: no product
                     const int cur = t & 1;
-                    if (cur) { ptx::mbar_wait(&h_full[1], hpar1); hpar1 ^= 1; }
-                    else     { ptx::mbar_wait(&h_full[0], hpar0); hpar0 ^= 1; }
-                    if (tbuf && blockIdx.x == 0 && (t == 20 || t == 21)) tbuf[(t - 20) * 4 + 0] = ptx::globaltimer_ns();
-                    ptx::tc_fence_after();
+                    const uint32_t hpar = cur ? hpar1 : hpar0;
+                    if (cur) hpar1 ^= 1; else hpar0 ^= 1;
+                    if constexpr (!PIPE) {
+                        ptx::mbar_wait(&h_full[cur], hpar);
+                        if (tbuf && blockIdx.x == 0 && iss == 0 && (t == 20 || t == 21)) tbuf[(t - 20) * 4 + 0] = ptx::globaltimer_ns();
+                        ptx::tc_fence_after();
+                    }
                     const uint32_t bb = sB_s + (uint32_t)cur * RU_B_BYTES;
 #pragma unroll
-                    for (int kb = 0; kb < 8; ++kb) {
+                    for (int kk = 0; kk < 8 / ISS; ++kk) {
+                        int kb = kb0 + kk;
+                        if constexpr (PIPE) {
+                            kb = (int)((rank - (uint32_t)kk) & (RU_CTAS - 1));      // arrival order: own tile, then rank-1, rank-2, ...
+                            ptx::mbar_wait(&hk_full[cur * RU_CTAS + kb], hpar);
+                            if (kk == 0 && tbuf && blockIdx.x == 0 && (t == 20 || t == 21)) tbuf[(t - 20) * 4 + 0] = ptx::globaltimer_ns();
+                            ptx::tc_fence_after();
+                        }
                         const uint64_t ad = umma_smem_desc(a0 + kb * RU_A_KB_BYTES);
                         const uint64_t bd = umma_smem_desc(bb + kb * RU_B_KB_BYTES);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            const uint32_t acc = (kk | k) ? 1u : 0u;
                             if constexpr (A_TMEM) {
                                 const uint32_t a_t = tmem_base + (uint32_t)(RU_A_COL0 + (kb * 4 + k) * 8);   // 16 k = 8 columns
-                                const uint32_t acc = (kb >= RU_NACC || k) ? 1u : 0u;
                                 asm volatile(
                                     "{\n\t.reg .pred p;\n\t"
                                     "setp.ne.b32 p, %4, 0;\n\t"
                                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                                    ::"r"(tmem_base + (uint32_t)((kb % RU_NACC) * 64)), "r"(a_t), "l"(bd + adv), "r"(idesc), "r"(acc) : "memory");
+                                    ::"r"(d_acc), "r"(a_t), "l"(bd + adv), "r"(idesc), "r"(acc) : "memory");
                             } else {
-                                ptx::umma_f16(tmem_base + (uint32_t)((kb % RU_NACC) * 64), ad + adv, bd + adv, idesc,
-                                              (kb >= RU_NACC || k) ? 1u : 0u);
+                                ptx::umma_f16(d_acc, ad + adv, bd + adv, idesc, acc);
                             }
                         }
                     }
+                    (void)kb1;
                     ptx::umma_commit(acc_full);
-                    if (tbuf && blockIdx.x == 0 && t == 20) tbuf[1] = ptx::globaltimer_ns();
+                    if (tbuf && blockIdx.x == 0 && iss == 0 && t == 20) tbuf[1] = ptx::globaltimer_ns();
                 }
             }
         } else {
@@ -202,7 +222,7 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
                     for (int j = 0; j < 12; ++j) s[j] = 0.f;
                     const uint32_t ta0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(12 * ch);
 #pragma unroll
-                    for (int a = 0; a < RU_NACC; ++a) {
+                    for (int a = 0; a < ISS; ++a) {
                         uint32_t r0[12], r1[12];
                         const uint32_t ta = ta0 + (uint32_t)(a * 64);
                         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
@@ -248,6 +268,20 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
                 if (tbuf && blockIdx.x == 0 && t == 20 && et == 0) tbuf[3] = ptx::globaltimer_ns();
                 if (t + 1 < L) {
                     // publish: local arrival + the 7 peers' bytes complete h_full[nxt] in every CTA
+                    if constexpr (PIPE) {
+                        if (et == 32) ptx::mbar_arrive(&hk_full[nxt * RU_CTAS + rank]);                 // own tile: written above
+                        else if (et >= 33 && et < 33 + RU_CTAS && (uint32_t)(et - 33) != rank)
+                            ptx::mbar_expect_tx(&hk_full[nxt * RU_CTAS + (et - 33)], RU_B_KB_BYTES);    // the tile source (et-33) will push
+                        if (et == 0) {
+                            const uint32_t src = ptx::smem_u32(tile);
+                            const uint32_t bar = ptx::smem_u32(&hk_full[nxt * RU_CTAS + rank]);
+#pragma unroll
+                            for (uint32_t c = 1; c < RU_CTAS; ++c) {
+                                const uint32_t dstc = (rank + c) & (RU_CTAS - 1);
+                                dsmem_bulk_push(map_to_cta(src, dstc), src, RU_B_KB_BYTES, map_to_cta(bar, dstc));
+                            }
+                        }
+                    } else {
                     if (et == 32) ptx::mbar_expect_tx(&h_full[nxt], RU_PUSH_BYTES);
                     if constexpr (ST_ASYNC) {
                         const uint32_t src = ptx::smem_u32(tile);
@@ -266,6 +300,7 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
                         const uint32_t src = ptx::smem_u32(tile);
                         dsmem_bulk_push(map_to_cta(src, (uint32_t)et), src, RU_B_KB_BYTES,
                                         map_to_cta(ptx::smem_u32(&h_full[nxt]), (uint32_t)et));
+                    }
                     }
                 }
                 // hs[b, t, 64c .. 64c+63] (hi / lo planes) from the tile: 16-byte chunks, un-swizzled
