@@ -103,3 +103,46 @@ def test_pybullet_shim_forward_kinematics():
     finally:
         sys.path.remove(os.path.join(ROOT, "oracle", "shims"))
         sys.modules.pop("pybullet", None)
+
+
+def test_product_state_to_row_matches_reference_runner(trace):
+    """Host logic of the product (tip_b200.streaming.state_to_row, used by StreamSession.set_state) against the row
+    the reference runner's constructor appended (record_state_aa_and_c(s_init, zeros), :47) and against later rows."""
+    from tip_b200.streaming import state_to_row
+    np.testing.assert_allclose(state_to_row(trace["s_init"], np.zeros(20)), trace["s_and_c_in"][0], atol=1e-12)
+    for t in (6, 40, 149):                         # rows the runner appended after frames t (closed loop)
+        i = t - 5                                  # model call index of runner call t
+        np.testing.assert_allclose(state_to_row(trace["qdq"][t], trace["ct"][t]), trace["s_and_c_in"][i + 1], atol=1e-12)
+
+
+def test_evaluator_bookkeeping_without_a_gpu(monkeypatch, trace):
+    """run_motions (row N4): stream/time bookkeeping with a fake session -- motions of different lengths, warm-up rows
+    hold s_init, finished motions are dropped, per-motion outputs come from their own stream."""
+    import tip_b200.evaluate as ev
+
+    class FakeSession:
+        def __init__(self, model, n_streams):
+            self.S, self.t, self.state_width = n_streams, 0, 80
+        def set_state(self, s):
+            assert s.shape == (self.S, 114)
+        def step_closed(self, frame, y_override=None):
+            self.t += 1
+            if self.t <= 5:
+                return None
+            out = np.zeros((self.S, 80))
+            out[:, 0] = frame[:, 0] * 10 + np.arange(self.S)          # depends on the stream's own frame only
+            out[:, 57] = 1.0
+            out[:, 77] = self.t
+            return out
+
+    monkeypatch.setattr(ev, "StreamSession", FakeSession)
+    imu = trace["imu"]
+    s0 = trace["s_init"]
+    res = ev.run_motions(None, [imu[:30], imu[:12], imu[:8]], [s0, s0, s0])
+    assert [r["state"].shape for r in res] == [(30, 57), (12, 57), (8, 57)]
+    for i, r in enumerate(res):
+        assert not r["valid"][:5].any() and r["valid"][5:].all()
+        np.testing.assert_array_equal(r["state"][:5], np.tile(s0[3:60], (5, 1)))
+        np.testing.assert_allclose(r["state"][5:, 0], imu[5:len(r["state"]), 0].astype(np.float32) * 10 + i, rtol=1e-6)
+        assert (r["ct"][5:, 0] == 1.0).all() and (r["ct"][:5] == 0).all()
+        np.testing.assert_array_equal(r["root_v"][5:, 0], np.arange(6, len(r["state"]) + 1))
