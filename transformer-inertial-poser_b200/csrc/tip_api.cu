@@ -510,6 +510,7 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
             cudaFuncSetAttribute(rnn_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM_BYTES);
             cudaFuncSetAttribute(rnn_umma_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM_BYTES);
             cudaFuncSetAttribute(rnn_umma_kernel<false, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM_BYTES);
+            cudaFuncSetAttribute(rnn_umma_kernel<false, false, 1, true, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM_BYTES);
             cudaLaunchConfig_t q{};
             q.gridDim = dim3(RU_CTAS * 18); q.blockDim = dim3(RU_THREADS); q.dynamicSmemBytes = RU_SMEM_BYTES;
             int n = 0;
@@ -526,9 +527,15 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
             const __half* wl = reinterpret_cast<const __half*>(m->blob + m->off.whh_lo);
             static const int st_async = getenv("TIP_RNN_STASYNC") ? atoi(getenv("TIP_RNN_STASYNC")) : 0;
             static const int iss2 = getenv("TIP_RNN_ISS2") ? atoi(getenv("TIP_RNN_ISS2")) : 0;
+            static const int nw20 = getenv("TIP_RNN_NW20") ? atoi(getenv("TIP_RNN_NW20")) : 1;
             static const int pipe = getenv("TIP_RNN_PIPE") ? atoi(getenv("TIP_RNN_PIPE")) : 1;     // pipelined all-gather (default)
             if (a_tmem)
                 launch_k(rnn_umma_kernel<true>, dim3(nc * RU_CTAS), dim3(RU_THREADS), RU_SMEM_BYTES, st,
+                    m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
+                    m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf, wh, wl);
+            else if (pipe && nw20 && (B + 19) / 20 <= m->rnn_umma_clusters)
+                // the batch fits the co-resident clusters with 20 windows each: smaller all-gather per step
+                launch_k(rnn_umma_kernel<false, false, 1, true, 20>, dim3(((B + 19) / 20) * RU_CTAS), dim3(RU_THREADS), RU_SMEM_BYTES, st,
                     m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
                     m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf, wh, wl);
             else if (pipe)

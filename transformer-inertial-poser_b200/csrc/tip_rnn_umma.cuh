@@ -53,7 +53,10 @@ constexpr int RU_A_COL0 = 64 * RU_NACC;              // first TMEM column of the
 // PIPE: one mbarrier per (parity, source CTA) instead of one per parity; every CTA pushes its tile to the peers in ring
 // order (rank+1 first) from ONE thread, so the tiles reach a CTA staggered in time (rank-1's first), and the issuer
 // consumes the k-blocks in that order: the MMAs of a step overlap the DSMEM all-gather instead of following it.
-template <bool A_TMEM, bool ST_ASYNC = false, int ISS = 1, bool PIPE = false>
+// NW windows per cluster (24 or 20): the all-gather moves NW * 64 units * 4 bytes per CTA pair and step and is what
+// paces a step, so when the batch fits the co-resident clusters either way the smaller group is faster (the MMA keeps
+// N = 48: B-tile rows [0, NW) = hi planes, [NW, 2 NW) = lo planes, the rest unused).
+template <bool A_TMEM, bool ST_ASYNC = false, int ISS = 1, bool PIPE = false, int NW = RU_N>
 __global__ void __cluster_dims__(RU_CTAS, 1, 1) __launch_bounds__(RU_THREADS, 1)
 rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
                 const float* __restrict__ gi, __half* __restrict__ hs_hi, __half* __restrict__ hs_lo,
@@ -69,6 +72,9 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
     uint64_t* acc_full = bars + 3;                         // MMAs of the step retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
     uint64_t* hk_full = bars + 8;                          // PIPE: [2 parities][8 source CTAs]
+    static_assert(NW == 24 || NW == 20, "window group: 24 or 20");
+    constexpr int WH = NW / 2, WL = NW / 4;                // windows per column half (warp group) / per lane
+    constexpr uint32_t PUSH_KB = 2 * NW * 128;             // bytes of a k-block tile that carry data (pushed to the peers)
     static_assert(!PIPE || (!ST_ASYNC && ISS == 1), "PIPE builds on the bulk-copy, single-issuer kernel");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,8 +147,8 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
     uint32_t hpar0 = 0, hpar1 = 0; // phase parities of h_full[0/1] (MMA issuer)
     uint32_t apar = 0;             // phase parity of acc_full (epilogue threads)
 
-    for (int rb = cluster_id; rb * RU_N < B; rb += n_clusters) {
-        const int b0 = rb * RU_N;
+    for (int rb = cluster_id; rb * NW < B; rb += n_clusters) {
+        const int b0 = rb * NW;
         if (warp == 0 || warp == 1 + RU_EPI_WARPS) {
             // ================= MMA issuer(s): warp 0 -> k-blocks [0, 8 / ISS), warp 9 -> the rest =================
             const int iss = (warp == 0) ? 0 : 1;
@@ -201,67 +207,82 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
             const int lh = lane >> 4;                            // 0: hi-row lane, 1: lo-row lane of the same unit
             const int ul = q * 16 + (lane & 15);                 // unit within the CTA
             const int unit = (int)rank * RU_UNITS + ul;
-            const int nb = 12 * ch + 6 * lh;                     // first of the 6 windows this lane finishes
+            const int nb = WH * ch + WL * lh;                    // first of the WL windows this lane finishes
             const float asc = __ldg(acc_scale);                  // 1 / (s_w * 16)
             const int et = (int)threadIdx.x - 32;                // 0..255 among the epilogue threads
             for (int t = 0; t < L; ++t) {
                 const int nxt = (t + 1) & 1;
-                float g[6];                                      // gi of this lane's outputs (latency overlaps the MMA wait)
+                float g[WL];                                     // gi of this lane's outputs (latency overlaps the MMA wait)
 #pragma unroll
-                for (int j = 0; j < 6; ++j)
+                for (int j = 0; j < WL; ++j)
                     g[j] = __ldg(gi + ((size_t)min(b0 + nb + j, B - 1) * L + t) * R + unit);
-                float pre[6];
+                float pre[WL];
                 if (t > 0) {
                     ptx::mbar_wait(acc_full, apar);
                     apar ^= 1;
                     if (tbuf && blockIdx.x == 0 && t == 20 && et == 0) tbuf[2] = ptx::globaltimer_ns();
                     ptx::tc_fence_after();
-                    // columns [12ch, 12ch+12) (x h_hi) and [24+12ch, ...) (x h_lo) of this lane's stacked row
-                    float s[12];
+                    // columns [WH ch, WH ch + WH) (x h_hi) and [NW + WH ch, ...) (x h_lo) of this lane's stacked row
+                    float s[WH];
 #pragma unroll
-                    for (int j = 0; j < 12; ++j) s[j] = 0.f;
-                    const uint32_t ta0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(12 * ch);
+                    for (int j = 0; j < WH; ++j) s[j] = 0.f;
+                    const uint32_t ta0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(WH * ch);
 #pragma unroll
                     for (int a = 0; a < ISS; ++a) {
                         uint32_t r0[12], r1[12];
                         const uint32_t ta = ta0 + (uint32_t)(a * 64);
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                                     : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]) : "r"(ta) : "memory");
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                     : "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]), "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11])
-                                     : "r"(ta + 4) : "memory");
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                                     : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]) : "r"(ta + 24) : "memory");
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                     : "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]), "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11])
-                                     : "r"(ta + 28) : "memory");
+                        // WH = 12: x4 + x8 columns; WH = 10: x8 + x2
+                        if constexpr (WH == 12) {
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]) : "r"(ta) : "memory");
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                         : "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]), "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11])
+                                         : "r"(ta + 4) : "memory");
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]) : "r"(ta + NW) : "memory");
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                         : "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]), "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11])
+                                         : "r"(ta + NW + 4) : "memory");
+                        } else {
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                         : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7])
+                                         : "r"(ta) : "memory");
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
+                                         : "=r"(r0[8]), "=r"(r0[9]) : "r"(ta + 8) : "memory");
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                         : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7])
+                                         : "r"(ta + NW) : "memory");
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
+                                         : "=r"(r1[8]), "=r"(r1[9]) : "r"(ta + NW + 8) : "memory");
+                        }
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int j = 0; j < 12; ++j) s[j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                        for (int j = 0; j < WH; ++j) s[j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
                     }
                     ptx::tc_fence_before();
-                    // fold the hi-row and lo-row lanes of a unit; lane half lh keeps windows 6lh..6lh+5
+                    // fold the hi-row and lo-row lanes of a unit; lane half lh keeps windows WL lh .. WL lh + WL - 1
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        const float mine = lh ? s[j + 6] : s[j];
-                        const float send = lh ? s[j] : s[j + 6];
+                    for (int j = 0; j < WL; ++j) {
+                        const float mine = lh ? s[j + WL] : s[j];
+                        const float send = lh ? s[j] : s[j + WL];
                         pre[j] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) pre[j] = 0.f;
+                    for (int j = 0; j < WL; ++j) pre[j] = 0.f;
                 }
                 // h_t -> this CTA's k-block of the next B operand (swizzled rows: windows hi, then windows lo)
                 uint8_t* tile = sB + nxt * RU_B_BYTES + (int)rank * RU_B_KB_BYTES;
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
+                for (int j = 0; j < WL; ++j) {
                     const int n = nb + j;
                     const float h = tanhf(fmaf(pre[j], asc, g[j]));
                     __half hi, lo;
                     half_split(h * ACT_SCALE, hi, lo);
-                    const int off = ((((ul >> 3) ^ (n & 7))) << 4) + (ul & 7) * 2;       // (24 + n) & 7 == n & 7
-                    *reinterpret_cast<__half*>(tile + n * 128 + off) = hi;
-                    *reinterpret_cast<__half*>(tile + (RU_N + n) * 128 + off) = lo;
+                    const int off_h = ((((ul >> 3) ^ (n & 7))) << 4) + (ul & 7) * 2;
+                    const int off_l = ((((ul >> 3) ^ ((NW + n) & 7))) << 4) + (ul & 7) * 2;
+                    *reinterpret_cast<__half*>(tile + n * 128 + off_h) = hi;
+                    *reinterpret_cast<__half*>(tile + (NW + n) * 128 + off_l) = lo;
                 }
                 ptx::fence_async_smem();                              // generic writes -> async proxy (MMA, bulk copies)
                 asm volatile("bar.sync 1, 256;" ::: "memory");        // the whole k-block is written
@@ -271,22 +292,22 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
                     if constexpr (PIPE) {
                         if (et == 32) ptx::mbar_arrive(&hk_full[nxt * RU_CTAS + rank]);                 // own tile: written above
                         else if (et >= 33 && et < 33 + RU_CTAS && (uint32_t)(et - 33) != rank)
-                            ptx::mbar_expect_tx(&hk_full[nxt * RU_CTAS + (et - 33)], RU_B_KB_BYTES);    // the tile source (et-33) will push
+                            ptx::mbar_expect_tx(&hk_full[nxt * RU_CTAS + (et - 33)], PUSH_KB);    // the tile source (et-33) will push
                         if (et == 0) {
                             const uint32_t src = ptx::smem_u32(tile);
                             const uint32_t bar = ptx::smem_u32(&hk_full[nxt * RU_CTAS + rank]);
 #pragma unroll
                             for (uint32_t c = 1; c < RU_CTAS; ++c) {
                                 const uint32_t dstc = (rank + c) & (RU_CTAS - 1);
-                                dsmem_bulk_push(map_to_cta(src, dstc), src, RU_B_KB_BYTES, map_to_cta(bar, dstc));
+                                dsmem_bulk_push(map_to_cta(src, dstc), src, PUSH_KB, map_to_cta(bar, dstc));
                             }
                         }
                     } else {
-                    if (et == 32) ptx::mbar_expect_tx(&h_full[nxt], RU_PUSH_BYTES);
+                    if (et == 32) ptx::mbar_expect_tx(&h_full[nxt], (RU_CTAS - 1) * PUSH_KB);
                     if constexpr (ST_ASYNC) {
                         const uint32_t src = ptx::smem_u32(tile);
                         const uint32_t bar = ptx::smem_u32(&h_full[nxt]);
-                        for (int i = et; i < RU_B_KB_BYTES / 16; i += 32 * RU_EPI_WARPS) {
+                        for (int i = et; i < (int)PUSH_KB / 16; i += 32 * RU_EPI_WARPS) {
                             const uint4 v = *reinterpret_cast<const uint4*>(tile + i * 16);
 #pragma unroll
                             for (uint32_t c = 1; c < RU_CTAS; ++c) {
@@ -298,15 +319,15 @@ rnn_umma_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
                         }
                     } else if (et < RU_CTAS && (uint32_t)et != rank) {
                         const uint32_t src = ptx::smem_u32(tile);
-                        dsmem_bulk_push(map_to_cta(src, (uint32_t)et), src, RU_B_KB_BYTES,
+                        dsmem_bulk_push(map_to_cta(src, (uint32_t)et), src, PUSH_KB,
                                         map_to_cta(ptx::smem_u32(&h_full[nxt]), (uint32_t)et));
                     }
                     }
                 }
                 // hs[b, t, 64c .. 64c+63] (hi / lo planes) from the tile: 16-byte chunks, un-swizzled
-                for (int i = et; i < 2 * RU_N * 8; i += 32 * RU_EPI_WARPS) {
+                for (int i = et; i < 2 * NW * 8; i += 32 * RU_EPI_WARPS) {
                     const int row = i >> 3, pc = i & 7, lc = pc ^ (row & 7);
-                    const int plane = row >= RU_N, n = row - plane * RU_N;
+                    const int plane = row >= NW, n = row - plane * NW;
                     if (b0 + n < B) {
                         const uint4 v = *reinterpret_cast<const uint4*>(tile + row * 128 + pc * 16);
                         __half* dst = (plane ? hs_lo : hs_hi) + ((size_t)(b0 + n) * L + t) * R + rank * RU_UNITS + lc * 8;
