@@ -449,6 +449,7 @@ static void launch_sgemm(tip_model* m, cudaStream_t st, const float* A, int lda,
 
 static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, float* out, float* out_lo,
                              int B, int L, float drop_p, uint64_t seed) {
+    pdl_kind() = 2;
     if (out_lo) {
         // tcgen05 engine: qkv and the output are FP16 hi/lo planes; warp-level tensor-core kernel
         static const int hpb = getenv("TIP_ATTN_HPB") ? atoi(getenv("TIP_ATTN_HPB")) : 8;
@@ -477,6 +478,7 @@ static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, fl
 }
 
 static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs, float* hs_lo, int B, int L) {
+    pdl_kind() = 4;
     if (m->rnn_clusters < 0) {
         // how many 8-CTA clusters the device can co-schedule (GPC layout dependent; 16..18 on B200)
         cudaFuncSetAttribute(rnn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RC_SMEM_BYTES);
@@ -626,6 +628,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
         float* xo = m->xin;
         float* xl = umma ? lo_xin : nullptr;
+        pdl_kind() = 8;
         launch_k(condition_kernel, dim3(blocks), dim3(256), 0, st, x_imu, x_s, keep_mask, past_scale, xo, xl, M,
                                                  d.n_imu, d.size_s, d.kin_pad, p_in, p_past, seed);
         m->launches++;
@@ -655,6 +658,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
                 gp.resid = gp.resid_lo = nullptr; gp.gamma = gp.beta = nullptr;
                 gp.out = m->gi; gp.out_lo = nullptr; gp.ldc = E;               // fp32 [rows][256]; gi is free until rnn_ih
                 umma_gemm(m->maps, which, layer, M, N, K, gp, false, st, 0, -1, true);
+                pdl_kind() = 8;
                 launch_k(resid_ln_kernel, dim3((M + 7) / 8), dim3(256), 0, st, m->gi, reinterpret_cast<const __half*>(ep.resid),
                                                              reinterpret_cast<const __half*>(ep.resid_lo), ep.gamma, ep.beta,
                                                              reinterpret_cast<__half*>(ep.out), reinterpret_cast<__half*>(ep.out_lo), 0, M);

@@ -118,7 +118,16 @@ inline int pdl_mode() {
     return v;
 }
 inline int& pdl_rows() { static int rows = 0; return rows; }     // rows of the forward being launched (set by the host path)
-inline bool pdl_enabled() { return pdl_mode() == 2 || (pdl_mode() == 1 && pdl_rows() <= 1024); }
+inline int& pdl_kind() { static int kind = 8; return kind; }     // 1 GEMM, 2 attention, 4 recurrence, 8 everything else
+inline int pdl_big_mask() {                                      // kernel kinds that use PDL in large forwards (experiment)
+    static const int v = getenv("TIP_PDL_BIG_MASK") ? atoi(getenv("TIP_PDL_BIG_MASK")) : 0;
+    return v;
+}
+inline bool pdl_enabled() {
+    if (pdl_mode() == 2) return true;
+    if (pdl_mode() != 1) return false;
+    return pdl_rows() <= 1024 || (pdl_big_mask() & pdl_kind()) != 0;
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};

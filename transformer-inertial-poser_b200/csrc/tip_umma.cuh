@@ -950,6 +950,7 @@ inline bool pair_mode() {      // experiment (TIP_PAIR=1): CTA-pair tiles for th
 // into the fp32 scratch `o_pre`; the caller follows with resid_ln_kernel.
 inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, const Epi& ep_in, bool ln,
                       cudaStream_t st, int m_tile0 = 0, int m_tile_cnt = -1, bool skinny = false) {
+    pdl_kind() = 1;
     const UmmaOperand *A = nullptr, *B = nullptr, *B256 = nullptr;
     const UmmaOutput* C = nullptr;
     switch (which) {
