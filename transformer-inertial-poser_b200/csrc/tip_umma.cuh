@@ -413,6 +413,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
             const int rbase = m0 + quarter * 32;                  // first row of this warp
             // lean path: full tile, vector stores, no dropout (warp-uniform); everything else -> slow path
             const bool fast = (m0 + UM_BM <= M) && (n0 + BN <= N) && vec_ok && !(ep.drop_p > 0.f) && !(ep.dbg & 7);
+            if constexpr (!LN) {
+                // this tile's bias slice (pre-multiplied by the output scale) -> shared memory while the MMAs still run:
+                // the kernel leaves ~3 KB of L1, so a __ldg in the chunk loop is an exposed L2 round trip
+                const int et = (int)threadIdx.x - 64;
+                if (et < BN) row_stat[(it & 1) * 256 + et] = (n0 + et < N) ? __ldg(ep.bias + n0 + et) * osc : 0.f;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             ptx::mbar_wait(&tfull_bar[as], aphase);
             if (warp == 2 && it == 0) TIP_TS(3);
             ptx::tc_fence_after();
@@ -424,57 +431,76 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                     // swizzled 4 KB shared tile, written to global by TMA (no transposition, no LSU stores)
                     const float sc = asc * osc;
                     uint8_t* sbuf = reinterpret_cast<uint8_t*>(stg);
+                    const float* bs = row_stat + (it & 1) * 256 + half * (BN / 2);
 #pragma unroll 1
                     for (int c = 0; c < CH; ++c) {
                         const int colb = n0 + half * (BN / 2) + c * 32;
                         ptx::tmem_ld32(t_acc + c * 32, v);
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + colb) + j4);   // warp-uniform
-                            v[4 * j4 + 0] = fmaxf(fmaf(v[4 * j4 + 0], sc, b.x * osc), relu_floor);
-                            v[4 * j4 + 1] = fmaxf(fmaf(v[4 * j4 + 1], sc, b.y * osc), relu_floor);
-                            v[4 * j4 + 2] = fmaxf(fmaf(v[4 * j4 + 2], sc, b.z * osc), relu_floor);
-                            v[4 * j4 + 3] = fmaxf(fmaf(v[4 * j4 + 3], sc, b.w * osc), relu_floor);
+                            const float4 b = *reinterpret_cast<const float4*>(bs + c * 32 + 4 * j4);       // broadcast
+                            v[4 * j4 + 0] = fmaxf(fmaf(v[4 * j4 + 0], sc, b.x), relu_floor);
+                            v[4 * j4 + 1] = fmaxf(fmaf(v[4 * j4 + 1], sc, b.y), relu_floor);
+                            v[4 * j4 + 2] = fmaxf(fmaf(v[4 * j4 + 2], sc, b.z), relu_floor);
+                            v[4 * j4 + 3] = fmaxf(fmaf(v[4 * j4 + 3], sc, b.w), relu_floor);
                         }
-                        if (lane == 0) ptx::bulk_wait_read0();        // previous box has left the shared tile
-                        __syncwarp();
                         if constexpr (OUT_HALF) {
-                            // two [32 rows][64 B] tiles (hi, lo), 64B-swizzled: chunk ^= (row >> 1) & 3
+                            // two [32 rows][64 B] tiles (hi, lo), 64B-swizzled: chunk ^= (row >> 1) & 3.  The two planes are
+                            // separate bulk groups, so while one plane's box is still being read out of shared memory
+                            // the other plane's tile can already be rewritten (wait_group.read 1, not 0).
                             const int sw = (lane >> 1) & 3;
+                            uint4 uh[4], ul[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                uint4 uh, ul;
                                 float h0, h1, l0, l1;
                                 __half2 t;
                                 veltkamp11(v[8 * j + 0], h0, l0); veltkamp11(v[8 * j + 1], h1, l1);
-                                t = __floats2half2_rn(h0, h1); uh.x = *reinterpret_cast<uint32_t*>(&t);
-                                t = __floats2half2_rn(l0, l1); ul.x = *reinterpret_cast<uint32_t*>(&t);
+                                t = __floats2half2_rn(h0, h1); uh[j].x = *reinterpret_cast<uint32_t*>(&t);
+                                t = __floats2half2_rn(l0, l1); ul[j].x = *reinterpret_cast<uint32_t*>(&t);
                                 veltkamp11(v[8 * j + 2], h0, l0); veltkamp11(v[8 * j + 3], h1, l1);
-                                t = __floats2half2_rn(h0, h1); uh.y = *reinterpret_cast<uint32_t*>(&t);
-                                t = __floats2half2_rn(l0, l1); ul.y = *reinterpret_cast<uint32_t*>(&t);
+                                t = __floats2half2_rn(h0, h1); uh[j].y = *reinterpret_cast<uint32_t*>(&t);
+                                t = __floats2half2_rn(l0, l1); ul[j].y = *reinterpret_cast<uint32_t*>(&t);
                                 veltkamp11(v[8 * j + 4], h0, l0); veltkamp11(v[8 * j + 5], h1, l1);
-                                t = __floats2half2_rn(h0, h1); uh.z = *reinterpret_cast<uint32_t*>(&t);
-                                t = __floats2half2_rn(l0, l1); ul.z = *reinterpret_cast<uint32_t*>(&t);
+                                t = __floats2half2_rn(h0, h1); uh[j].z = *reinterpret_cast<uint32_t*>(&t);
+                                t = __floats2half2_rn(l0, l1); ul[j].z = *reinterpret_cast<uint32_t*>(&t);
                                 veltkamp11(v[8 * j + 6], h0, l0); veltkamp11(v[8 * j + 7], h1, l1);
-                                t = __floats2half2_rn(h0, h1); uh.w = *reinterpret_cast<uint32_t*>(&t);
-                                t = __floats2half2_rn(l0, l1); ul.w = *reinterpret_cast<uint32_t*>(&t);
-                                const int off = lane * 64 + ((j ^ sw) << 4);
-                                *reinterpret_cast<uint4*>(sbuf + off) = uh;
-                                *reinterpret_cast<uint4*>(sbuf + 2048 + off) = ul;
+                                t = __floats2half2_rn(h0, h1); uh[j].w = *reinterpret_cast<uint32_t*>(&t);
+                                t = __floats2half2_rn(l0, l1); ul[j].w = *reinterpret_cast<uint32_t*>(&t);
+                            }
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // hi tile free
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((j ^ sw) << 4)) = uh[j];
+                            ptx::fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                ptx::tma_store_2d(&mapC0, sbuf, colb, rbase);
+                                ptx::bulk_commit();
+                                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");              // lo tile free
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(sbuf + 2048 + lane * 64 + ((j ^ sw) << 4)) = ul[j];
+                            ptx::fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                ptx::tma_store_2d(&mapC1, sbuf + 2048, colb, rbase);
+                                ptx::bulk_commit();
                             }
                         } else {
+                            if (lane == 0) ptx::bulk_wait_read0();        // previous box has left the shared tile
+                            __syncwarp();
                             // one [32 rows][128 B] fp32 tile, 128B-swizzled: chunk ^= row & 7
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
                                 *reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
                                     make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        }
-                        ptx::fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            ptx::tma_store_2d(&mapC0, sbuf, colb, rbase);
-                            if constexpr (OUT_HALF) ptx::tma_store_2d(&mapC1, sbuf + 2048, colb, rbase);
-                            ptx::bulk_commit();
+                            ptx::fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                ptx::tma_store_2d(&mapC0, sbuf, colb, rbase);
+                                ptx::bulk_commit();
+                            }
                         }
                     }
                 } else if (fast) {
