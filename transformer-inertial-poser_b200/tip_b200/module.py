@@ -12,6 +12,7 @@ There is no CPU path: calling the module with CPU tensors raises.
 from __future__ import annotations
 
 import ctypes as C
+import operator
 import math
 
 import torch
@@ -37,6 +38,9 @@ def state_dict_keys(tf_layers: int = 4, with_rnn: bool = True):
 
 class _Bag(nn.Module):
     """Parameter container; exists only so state_dict keys match the reference's."""
+
+
+_VERSION_OF = operator.attrgetter("_version")
 
 
 def _linear_bag(n_out: int, n_in: int, gen: torch.Generator) -> _Bag:
@@ -118,6 +122,7 @@ class TF_RNN_Past_State(nn.Module):
         self._handle = None
         self._device = None
         self._packed_sig = None
+        self._packed_versions = None
         self._plist = None
 
     # -------------------------------------------------------------------------------------------
@@ -141,9 +146,11 @@ class TF_RNN_Past_State(nn.Module):
         except Exception:
             pass
 
-    def _ensure(self, device: torch.device):
+    def _ensure(self, device: torch.device, fast: bool = False):
         """Create the C handle on ``device`` and (re)pack when any parameter changed
-        (load_state_dict, .cuda(), in-place optimiser updates bump ``_version``)."""
+        (load_state_dict, .cuda(), in-place optimiser updates bump ``_version``).  ``fast`` (the streaming
+        session's per-frame calls): compare the version counters only; storage swaps through ``_apply`` reset
+        the signature, a bare ``param.data = tensor`` is picked up by the next full check (any ``forward``)."""
         if self._lib is None:
             self._lib = capi.load_library()
         if self._handle is None or self._device != device:
@@ -154,6 +161,9 @@ class TF_RNN_Past_State(nn.Module):
                 capi.check(self._lib, None, rc, "tip_create")
             self._handle, self._device = h, device
         params = self._ordered_params()
+        if fast and self._packed_versions is not None and self._packed_sig is not None and \
+                tuple(map(_VERSION_OF, params)) == self._packed_versions:
+            return self._handle          # per-frame callers: version counters only (6 us instead of 15 us of Python)
         sig = tuple((p.data_ptr(), p._version) for p in params)
         if sig != self._packed_sig:
             for p in params:
@@ -170,7 +180,14 @@ class TF_RNN_Past_State(nn.Module):
                 rc = self._lib.tip_pack_weights(self._handle, ptrs, numels, n, C.c_void_p(stream))
             capi.check(self._lib, self._handle, rc, "tip_pack_weights")
             self._packed_sig = sig
+        self._packed_versions = tuple(map(_VERSION_OF, params))
         return self._handle
+
+    def _apply(self, fn, *args, **kwargs):
+        # .cuda() / .to() / .float(): parameter storage may move without a version bump
+        self._packed_sig = None
+        self._packed_versions = None
+        return super()._apply(fn, *args, **kwargs)
 
     def _dropout_struct(self):
         p_enc = self.ENCODER_DROPOUT if self.training else 0.0
@@ -229,7 +246,7 @@ class TF_RNN_Past_State(nn.Module):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("forward_host: move the module to a CUDA device first (.cuda())")
-        h = self._ensure(dev)
+        h = self._ensure(dev, fast=True)
         xi = torch.as_tensor(x_imu, dtype=torch.float32).contiguous()
         xs = torch.as_tensor(x_s, dtype=torch.float32).contiguous()
         if xi.is_cuda or xs.is_cuda:

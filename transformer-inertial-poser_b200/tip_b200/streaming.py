@@ -42,7 +42,7 @@ class StreamSession:
         """imu_row (S, 72|90), s_row (S, size_s): numpy / CPU tensors (copied in, result returned
         as numpy after a stream sync) or CUDA tensors (asynchronous, CUDA tensor returned)."""
         m = self.model
-        h = m._ensure(self.device)
+        h = m._ensure(self.device, fast=True)
         S = self.n_streams
         on_host = not (isinstance(imu_row, torch.Tensor) and imu_row.is_cuda)
         if on_host:
@@ -69,7 +69,7 @@ class StreamSession:
         rotation and the acc-sum feature run on the device.  Returns None for the first 5 calls (the
         runner returns ``s_init`` then, :125-128), afterwards ``y[:, L-1, :]`` like ``step``."""
         m = self.model
-        h = m._ensure(self.device)
+        h = m._ensure(self.device, fast=True)
         S = self.n_streams
         on_host = not (isinstance(raw_imu, torch.Tensor) and raw_imu.is_cuda)
         if on_host:
@@ -117,7 +117,7 @@ class StreamSession:
         5 warm-up calls.  The state row is fed back to the model on the device (no per-frame x_s upload).
         ``y_override`` (S, size_s) teacher-forces the post step (parity-test hook)."""
         m = self.model
-        h = m._ensure(self.device)
+        h = m._ensure(self.device, fast=True)
         S, W = self.n_streams, self.state_width
         on_host = not (isinstance(raw_imu, torch.Tensor) and raw_imu.is_cuda)
         keep = None
