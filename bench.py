@@ -339,6 +339,22 @@ def main():
                                              "window shift, forward B=1 L=40, device post-model step + state feedback, "
                                              "D2H of the (80,) float64 pose row, stream sync"}
 
+        # 64 recorded motions evaluated as parallel streams of one closed-loop session (row N4): frames/s over all streams
+        S = 64
+        sess3 = StreamSession(model, n_streams=S)
+        sess3.set_state(np.tile(s0, (S, 1)))
+        rots = Rotation.random(6 * S, random_state=4)
+        raw = np.concatenate((rots.as_matrix().reshape(S, 54), 3.0 * rs.standard_normal((S, 18))), axis=1).astype(np.float32)
+        for t in range(60):                                   # ramp the windows to L = 40
+            sess3.step_closed(raw)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in range(200):
+            st = sess3.step_closed(raw)
+        el = time.perf_counter() - t0
+        stream_lat["multi_stream_closed_loop"] = {"streams": S, "frames": 200, "frames_per_s": S * 200 / el,
+                                                  "ms_per_frame_all_streams": 1e3 * el / 200, "finite": bool(np.isfinite(st).all())}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
