@@ -159,8 +159,10 @@ def test_forward_host_entry():
 
 
 def test_forward_host_pipelined_matches_device_call():
-    """B >= 64 takes the pipelined host entry (chunked H2D + conditioning, chunked head + D2H);
-    pinned and pageable buffers must give the device call's result bit for bit."""
+    """B >= 64 takes the two-part host pipeline (upload / forward / download of two half batches overlapped).  Pinned
+    and pageable buffers must give the same result bit for bit; against the device call the two half-batch forwards
+    may take a different LayerNorm-GEMM path than the whole batch (un-fused below 74 row tiles), so that comparison
+    is to fp32 round-off, and every result is checked against the oracle."""
     sd = O.random_state_dict(30)
     m = make_model(sd)
     for B, L in ((256, 40), (70, 33), (64, 1)):
@@ -170,10 +172,12 @@ def test_forward_host_pipelined_matches_device_call():
         out = torch.empty((B, L, 131)).pin_memory()
         y_pinned = m.forward_host(torch.from_numpy(x_imu).pin_memory(), torch.from_numpy(x_s).pin_memory(), out=out)
         assert y_pinned is out
-        np.testing.assert_array_equal(y_pageable, y_dev)
-        np.testing.assert_array_equal(out.numpy(), y_dev)
-    ref = O.forward(sd, x_imu, x_s)
-    assert np.abs(y_dev - ref).max() < TOL
+        np.testing.assert_array_equal(y_pageable, out.numpy())
+        assert np.abs(out.numpy() - y_dev).max() < 2e-5
+        y_again = m.forward_host(x_imu, x_s).numpy()                 # graph replay of both parts
+        np.testing.assert_array_equal(y_again, y_pageable)
+        ref = O.forward(sd, x_imu, x_s)
+        assert np.abs(y_dev - ref).max() < TOL and np.abs(y_pageable - ref).max() < TOL
 
 
 def test_repack_on_load_state_dict_and_param_update():

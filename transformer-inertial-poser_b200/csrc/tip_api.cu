@@ -62,7 +62,7 @@ struct tip_model {
     int cap_rows = 0;
     float* ws = nullptr;
     float *xin = nullptr, *xa = nullptr, *xb = nullptr, *qkv = nullptr, *att = nullptr,
-          *hid = nullptr, *gi = nullptr, *hs = nullptr;
+          *hid = nullptr, *gi = nullptr, *hs = nullptr, *pre = nullptr;   // pre: fp32 [rows][256] scratch of the un-fused LayerNorm path
     size_t plane_xin = 0, plane_e = 0, plane_f = 0, plane_r = 0;   // elements per plane (= hi->lo stride in halves)
     UmmaMaps maps;            // TMA descriptors of the workspace + weights (tcgen05 engine)
     bool maps_ready = false;
@@ -433,7 +433,7 @@ static int ensure_workspace(tip_model* m, int rows) {
     // one fp32 plane per activation; the tcgen05 engine uses the same bytes as two fp16 planes (hi, lo)
     const size_t o_xin = take(m->plane_xin), o_xa = take(m->plane_e), o_xb = take(m->plane_e),
                  o_qkv = take((size_t)cap * 3 * E), o_att = take(m->plane_e),
-                 o_hid = take(m->plane_f), o_gi = take(m->plane_r), o_hs = take(m->plane_r);
+                 o_hid = take(m->plane_f), o_gi = take(m->plane_r), o_hs = take(m->plane_r), o_pre = take(m->plane_e);
     cudaError_t e = cudaMalloc(&m->ws, p * sizeof(float));
     if (e != cudaSuccess) {
         m->set_error(std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e));
@@ -441,7 +441,7 @@ static int ensure_workspace(tip_model* m, int rows) {
     }
     cudaMemset(m->ws, 0, p * sizeof(float));
     m->xin = m->ws + o_xin; m->xa = m->ws + o_xa; m->xb = m->ws + o_xb; m->qkv = m->ws + o_qkv;
-    m->att = m->ws + o_att; m->hid = m->ws + o_hid; m->gi = m->ws + o_gi; m->hs = m->ws + o_hs;
+    m->att = m->ws + o_att; m->hid = m->ws + o_hid; m->gi = m->ws + o_gi; m->hs = m->ws + o_hs; m->pre = m->ws + o_pre;
     m->cap_rows = cap;
     m->maps_ready = false;
     drop_graphs(m);
@@ -627,7 +627,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
     if (umma) {
         if (!m->maps_ready) {
             rc = umma_build_maps(m->maps, m->blob, o, d, m->xin, m->plane_xin, m->xa, m->xb, m->att,
-                                 m->plane_e, m->hid, m->plane_f, m->hs, m->plane_r, m->qkv, m->gi, m->cap_rows, m->err);
+                                 m->plane_e, m->hid, m->plane_f, m->hs, m->plane_r, m->qkv, m->gi, m->pre, m->cap_rows, m->err);
             if (rc != TIP_OK) return rc;
             m->maps_ready = true;
         }
@@ -670,16 +670,20 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
                 ep.tbuf = tb + 8 * (which + (layer > 0 ? 16 : 0));
                 g_tbuf = tb;
             }
-            // small M: one CTA per 128-row tile would stream the whole weight matrix through a single SM (ff2: 17 us);
-            // split the columns over 4 CTAs (64-column tiles into the fp32 scratch) and normalise in a second, tiny kernel
-            static const int skinny_tiles = getenv("TIP_SKINNY_TILES") ? atoi(getenv("TIP_SKINNY_TILES")) : 8;
+            // The fused LayerNorm GEMM needs whole rows per CTA, i.e. ONE CTA per 128-row tile: with few row tiles most SMs
+            // idle while each busy one streams the whole weight matrix (ff2: 17 us per tile).  Up to 74 row tiles
+            // (4 x 74 = two full waves of 148 CTAs) it is faster to split the columns over 4 CTAs (64-column tiles into
+            // the fp32 scratch) and normalise in a second, small kernel.  Measured forward, un-fused vs fused: B = 1
+            // 328 vs 401 us, 32: 303 vs 373, 64: 321 vs 387, 96: 350 vs 412, 128: 393 vs 412, 192: 444 vs 459;
+            // B = 256 (80 tiles = 320 CTAs = three waves): 549 vs 514, so the fused kernel keeps the big batches.
+            static const int skinny_tiles = getenv("TIP_SKINNY_TILES") ? atoi(getenv("TIP_SKINNY_TILES")) : 74;
             if (ln && TN <= skinny_tiles) {
                 Epi gp = ep;
                 gp.resid = gp.resid_lo = nullptr; gp.gamma = gp.beta = nullptr;
-                gp.out = m->gi; gp.out_lo = nullptr; gp.ldc = E;               // fp32 [rows][256]; gi is free until rnn_ih
+                gp.out = m->pre; gp.out_lo = nullptr; gp.ldc = E;              // fp32 [rows][256] scratch (its own buffer: batch parts may overlap)
                 umma_gemm(m->maps, which, layer, M, N, K, gp, false, st, T0, TN, true);
                 pdl_kind() = 8;
-                launch_k(resid_ln_kernel, dim3((M - R0 + 7) / 8), dim3(256), 0, st, m->gi, reinterpret_cast<const __half*>(ep.resid),
+                launch_k(resid_ln_kernel, dim3((M - R0 + 7) / 8), dim3(256), 0, st, m->pre, reinterpret_cast<const __half*>(ep.resid),
                                                              reinterpret_cast<const __half*>(ep.resid_lo), ep.gamma, ep.beta,
                                                              reinterpret_cast<__half*>(ep.out), reinterpret_cast<__half*>(ep.out_lo), R0, M - R0);
                 m->launches += 2;
@@ -1045,7 +1049,7 @@ static int stream_step_core(tip_model* m, float* y_last, int rows_on_host, const
             if ((m->engine == 2 || (m->engine == 0 && UMMA_AVAILABLE)) && !m->maps_ready) {
                 // descriptors must exist before capture (their creation is host work)
                 rc = umma_build_maps(m->maps, m->blob, m->off, m->d, m->xin, m->plane_xin, m->xa, m->xb, m->att,
-                                     m->plane_e, m->hid, m->plane_f, m->hs, m->plane_r, m->qkv, m->gi, m->cap_rows, m->err);
+                                     m->plane_e, m->hid, m->plane_f, m->hs, m->plane_r, m->qkv, m->gi, m->pre, m->cap_rows, m->err);
                 if (rc != TIP_OK) return rc;
                 m->maps_ready = true;
             }

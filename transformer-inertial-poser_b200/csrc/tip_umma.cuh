@@ -895,7 +895,7 @@ inline bool umma_make_store_map(CUtensorMap* map, void* base, bool is_half, uint
 
 inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, const Dims& d, float* xin,
                            size_t plane_xin, float* xa, float* xb, float* att, size_t plane_e, float* hid,
-                           size_t plane_f, float* hs, size_t plane_r, float* qkv, float* gi, int cap_rows,
+                           size_t plane_f, float* hs, size_t plane_r, float* qkv, float* gi, float* pre, int cap_rows,
                            std::string& err) {
     bool ok = true;
     auto outp = [&](UmmaOutput& op, float* p, size_t plane, int cols, bool is_half) {
@@ -913,7 +913,7 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
     outp(mp.o_hid, hid, plane_f, F, true);
     outp(mp.o_qkv, qkv, (size_t)cap_rows * 3 * E, 3 * E, true);      // FP16 hi/lo planes of 16*q|k|v for the mma attention
     outp(mp.o_gi, gi, 0, R, false);
-    outp(mp.o_pre, gi, 0, E, false);         // same memory as gi (free until rnn_ih), viewed as [rows][256]
+    outp(mp.o_pre, pre, 0, E, false);        // fp32 [rows][256] scratch of the un-fused LayerNorm path
     // activation planes: hi at the start of the buffer, lo `plane` halves later (same bytes as one fp32 plane)
     auto act = [&](UmmaOperand& op, const float* p, size_t plane, int cols) {
         const __half* h = reinterpret_cast<const __half*>(p);
