@@ -39,16 +39,16 @@ CKPT = os.path.join(ROOT, "baseline", "_ref", "model-with-dip9and10.pt")
 def load_weights():
     """Released checkpoint when staged (baseline/_ref, copied by build()), else seeded random
     weights of the same architecture."""
-    from oracle import tip_oracle as O          # weight/input generators only (synthetic data)
+    from tip_b200 import synthetic as S         # product-side generators (no oracle on the measured arm)
     if os.path.exists(CKPT):
         sd = {k: v.numpy() for k, v in torch.load(CKPT, map_location="cpu").items()}
         return sd, "checkpoint model-with-dip9and10.pt"
-    return O.random_state_dict(11), "random-init (seed 11)"
+    return S.random_state_dict(11), "random-init (seed 11)"
 
 
 def synth(seed, B):
-    from oracle import tip_oracle as O
-    return O.synth_inputs(seed, B, L_WIN)
+    from tip_b200 import synthetic as S
+    return S.synth_inputs(seed, B, L_WIN)
 
 
 def measured_peaks():

@@ -104,3 +104,16 @@ def test_torch_port_matches_reference_golden(name):
     sd, kw = _weights(g)
     y = OT.forward(OT.to_torch_state(sd), g["x_imu"], g["x_s"], **kw).numpy()
     assert np.abs(y - g["y"]).max() < TOL
+
+
+def test_product_synthetic_generators_match_the_oracle_copies():
+    """bench.py's measured arm draws its weights / inputs from tip_b200.synthetic (no oracle import on the product
+    side); the oracle keeps its own copy -- they must stay identical."""
+    from tip_b200 import synthetic as S
+    for seed, B, L in ((1, 3, 40), (9, 2, 7)):
+        a, b = O.synth_inputs(seed, B, L), S.synth_inputs(seed, B, L)
+        assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a, b))
+    for kw in (dict(), dict(size_s=119), dict(with_rnn=False), dict(with_acc_sum=False)):
+        sa, sb = O.random_state_dict(4, **kw), S.random_state_dict(4, **kw)
+        assert list(sa) == list(sb) and all(np.array_equal(sa[k], sb[k]) for k in sa)
+    assert S.state_dict_keys() == O.state_dict_keys()
