@@ -121,13 +121,15 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
             }
         }
         // mask (key <= query, key < L), un-scale (planes carry 16*q and 16*k), row max over the quad
+        // (key tiles beyond the causal range of this row tile are skipped at compile time: their probabilities are 0)
         float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 6; ++nt) {
+            if (!(nt <= 2 * mt + 1 && nt < 5)) continue;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int key = 8 * nt + 2 * t4 + e;
-                const bool live = (nt <= 2 * mt + 1) && (nt < 5) && key < L;
+                const bool live = key < L;
                 s[nt][e] = (live && key <= ra) ? s[nt][e] * (1.f / (ACT_SCALE * ACT_SCALE)) : -INFINITY;
                 s[nt][2 + e] = (live && key <= rb) ? s[nt][2 + e] * (1.f / (ACT_SCALE * ACT_SCALE)) : -INFINITY;
                 ma = fmaxf(ma, s[nt][e]);
@@ -140,6 +142,7 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
         float la = 0.f, lb = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 6; ++nt) {
+            if (!(nt <= 2 * mt + 1 && nt < 5)) continue;         // s[nt] stays 0 there: contributes nothing to P V
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int key = 8 * nt + 2 * t4 + e;
