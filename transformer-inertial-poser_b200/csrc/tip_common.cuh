@@ -117,8 +117,8 @@ inline int pdl_mode() {
     static const int v = getenv("TIP_PDL") ? atoi(getenv("TIP_PDL")) : 1;
     return v;
 }
-inline int& pdl_rows() { static int rows = 0; return rows; }     // rows of the forward being launched (set by the host path)
-inline int& pdl_kind() { static int kind = 8; return kind; }     // 1 GEMM, 2 attention, 4 recurrence, 8 everything else
+inline int& pdl_rows() { static thread_local int rows = 0; return rows; }     // rows of the forward being launched (set by the host path)
+inline int& pdl_kind() { static thread_local int kind = 8; return kind; }     // 1 GEMM, 2 attention, 4 recurrence, 8 everything else
 inline int pdl_big_mask() {                                      // kernel kinds that use PDL in large forwards (experiment)
     static const int v = getenv("TIP_PDL_BIG_MASK") ? atoi(getenv("TIP_PDL_BIG_MASK")) : 0;
     return v;
