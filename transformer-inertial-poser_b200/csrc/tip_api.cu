@@ -79,8 +79,7 @@ struct tip_model {
     double* acc_ring = nullptr;
     int n_raw = 0, n_rows = 0;
     // N3: post-model step state (closed loop)
-    float* fb_s = nullptr;                 // (S, size_s) row fed back as the next x_s row
-    double *pp_ring = nullptr, *pp_last = nullptr, *pp_out = nullptr, *h_pp_out = nullptr;
+    double *pp_ring = nullptr, *pp_last = nullptr, *pp_out = nullptr, *h_pp_out = nullptr;   // the fed-back x_s row lives in st_rows
     int n_post = 0;
     bool fb_set = false;
     cudaGraphExec_t st_graph = nullptr;   // captured steady-state step (L == MAXL)
@@ -213,7 +212,6 @@ static void free_stream_state(tip_model* m) {
     drop_graphs(m);
     if (m->acc_ring) { cudaFree(m->acc_ring); m->acc_ring = nullptr; }
     if (m->h_raw) { cudaFreeHost(m->h_raw); m->h_raw = nullptr; }
-    if (m->fb_s) { cudaFree(m->fb_s); m->fb_s = nullptr; }
     for (double** p : {&m->pp_ring, &m->pp_last, &m->pp_out})
         if (*p) { cudaFree(*p); *p = nullptr; }
     if (m->h_pp_out) { cudaFreeHost(m->h_pp_out); m->h_pp_out = nullptr; }
@@ -990,12 +988,10 @@ extern "C" int tip_stream_reset(tip_model* m, int n_streams) {
     TIP_CUDA_TRY(m, cudaMalloc(&m->acc_ring, S * ACC_WIN * 18 * sizeof(double)));
     TIP_CUDA_TRY(m, cudaMallocHost(&m->h_raw, S * IMU_RAW * sizeof(float)));
     const size_t out_w = 60 + (d.size_s - 111);
-    TIP_CUDA_TRY(m, cudaMalloc(&m->fb_s, S * d.size_s * sizeof(float)));
     TIP_CUDA_TRY(m, cudaMalloc(&m->pp_ring, S * PP_TAPS * d.size_s * sizeof(double)));
     TIP_CUDA_TRY(m, cudaMalloc(&m->pp_last, S * PP_TAIL * sizeof(double)));
     TIP_CUDA_TRY(m, cudaMalloc(&m->pp_out, S * out_w * sizeof(double)));
     TIP_CUDA_TRY(m, cudaMallocHost(&m->h_pp_out, S * out_w * sizeof(double)));
-    TIP_CUDA_TRY(m, cudaMemset(m->fb_s, 0, S * d.size_s * sizeof(float)));
     TIP_CUDA_TRY(m, cudaMemset(m->win_imu, 0, S * MAXL * d.n_imu * sizeof(float)));
     TIP_CUDA_TRY(m, cudaMemset(m->win_s, 0, S * MAXL * d.size_s * sizeof(float)));
     m->n_streams = n_streams;
@@ -1012,12 +1008,12 @@ static int stream_step_device(tip_model* m, const tip_dropout* drop, cudaStream_
     pdl_rows() = S * MAXL;
     const float* imu_rows = m->st_rows;
     const float* s_rows = m->st_rows + (size_t)S * d.n_imu;
-    launch_k(window_push_kernel, dim3(S), dim3(256), 0, st, m->win_imu, imu_rows, d.n_imu, len_before);
-    launch_k(window_push_kernel, dim3(S), dim3(256), 0, st, m->win_s, s_rows, d.size_s, len_before);
-    m->launches += 2;
+    pdl_kind() = 8;
+    launch_k(window_push_kernel, dim3(S, 2), dim3(256), 0, st, m->win_imu, imu_rows, d.n_imu, m->win_s, s_rows, d.size_s, len_before);
+    m->launches += 1;
     const int L = std::min(len_before + 1, MAXL);
     const float *xi = m->win_imu, *xs = m->win_s;
-    int extra = 2;
+    int extra = 1;
     if (L < MAXL) {
         const int64_t ti = (int64_t)S * L * d.n_imu, ts = (int64_t)S * L * d.size_s;
         launch_k(window_compact_kernel, dim3((unsigned)std::min<int64_t>((ti + 255) / 256, 1184)), dim3(256), 0, st, m->win_imu, m->st_ximu, S, L, d.n_imu);
@@ -1153,10 +1149,10 @@ extern "C" int tip_stream_set_state(tip_model* m, const float* s_row0, int rows_
     const size_t bytes = (size_t)m->n_streams * m->d.size_s * sizeof(float);
     if (rows_on_host) {
         memcpy(m->h_rows, s_row0, bytes);
-        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->fb_s, m->h_rows, bytes, cudaMemcpyHostToDevice, st));
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows + (size_t)m->n_streams * m->d.n_imu, m->h_rows, bytes, cudaMemcpyHostToDevice, st));
         TIP_CUDA_TRY(m, cudaStreamSynchronize(st));
     } else {
-        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->fb_s, s_row0, bytes, cudaMemcpyDeviceToDevice, st));
+        TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows + (size_t)m->n_streams * m->d.n_imu, s_row0, bytes, cudaMemcpyDeviceToDevice, st));
     }
     m->fb_set = true;
     return TIP_OK;
@@ -1182,8 +1178,7 @@ extern "C" int tip_stream_step_closed(tip_model* m, const float* raw_imu, const 
     } else {
         TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_raw, raw_imu, n_r * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    // the x_s row of this call is the one the previous post step produced (or the initial state)
-    TIP_CUDA_TRY(m, cudaMemcpyAsync(m->st_rows + n_i, m->fb_s, n_s * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // the x_s row of this call is the one the previous post step (or tip_stream_set_state) left in the staging rows
     launch_k(imu_push_kernel, dim3((unsigned)S), dim3(32), 0, st, m->st_raw, m->raw_ring, m->acc_ring, m->st_rows, d.n_imu, m->n_raw, m->n_rows);
     TIP_CUDA_TRY(m, cudaGetLastError());
     m->n_raw += (m->n_raw == 0) ? IMU_DELAY + 1 : 1;
@@ -1202,7 +1197,7 @@ extern "C" int tip_stream_step_closed(tip_model* m, const float* raw_imu, const 
                                         rows_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
         ysrc = m->st_y;
     }
-    launch_k(post_step_kernel, dim3((unsigned)S), dim3(32), 0, st, ysrc, m->st_rows, d.n_imu, m->pp_ring, m->pp_last, m->fb_s, m->pp_out,
+    launch_k(post_step_kernel, dim3((unsigned)S), dim3(32), 0, st, ysrc, m->st_rows, d.n_imu, m->pp_ring, m->pp_last, m->st_rows + n_i, m->pp_out,
                                                  d.size_s, m->n_post);
     TIP_CUDA_TRY(m, cudaGetLastError());
     m->launches += 2;                       // imu_push + post_step

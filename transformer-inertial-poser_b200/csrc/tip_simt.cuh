@@ -787,10 +787,15 @@ rnn_small_kernel(const float* __restrict__ gi, const float* __restrict__ whh,
 // (in place: every thread first reads its elements, the CTA synchronises, then writes them one row
 // earlier -- coalesced both ways), then append the new row.  One CTA per stream and window.
 __global__ void __launch_bounds__(256)
-window_push_kernel(float* __restrict__ win, const float* __restrict__ new_row, int width, int len) {
+window_push_kernel(float* __restrict__ win0, const float* __restrict__ new_row0, int width0,
+                   float* __restrict__ win1, const float* __restrict__ new_row1, int width1, int len) {
     griddep_wait();
     griddep_launch();
+    // blockIdx.y selects the window set (0: IMU rows, 1: state rows) -- both windows of a frame in one launch.
     // win: (S, MAXL, width); len = rows currently held (same for every stream)
+    float* win = blockIdx.y ? win1 : win0;
+    const float* new_row = blockIdx.y ? new_row1 : new_row0;
+    const int width = blockIdx.y ? width1 : width0;
     float* w = win + (size_t)blockIdx.x * MAXL * width;
     const float* nr = new_row + (size_t)blockIdx.x * width;
     constexpr int PER = (MAXL * 160 + 255) / 256;   // width <= 160
