@@ -111,6 +111,21 @@ int  tip_forward(tip_model* m, const float* x_imu_dev, const float* x_s_dev, flo
 int  tip_forward_host(tip_model* m, const float* x_imu_host, const float* x_s_host, float* y_host,
                       int B, int L, int last_row_only, const tip_dropout* drop, void* stream);
 
+/* The same job split into submit + wait, for callers that have the next batch ready before they need
+ * the previous result (offline_testing_simple.py:360-399 walks recorded motions whose inputs are all
+ * known up front; the reference runs them one blocking call at a time).  `slot` (0 <=
+ * slot < TIP_HOST_SLOTS) names one of the handle's job slots, each with its own device staging:
+ * submit queues upload -> forward -> download on the handle's three internal streams and returns at
+ * once; uploads, forwards and downloads of different slots overlap (forwards themselves run one
+ * after another: they share the workspace).  wait(slot) blocks until y_host of that slot's job is
+ * complete; submitting to a busy slot waits for it first.  The three host buffers MUST be
+ * page-locked (TIP_ERR_INVALID_ARG otherwise) and must stay untouched until wait returns.  Until
+ * every submitted slot has been waited for, no other entry point may be called on this handle. */
+#define TIP_HOST_SLOTS 4
+int  tip_forward_host_submit(tip_model* m, int slot, const float* x_imu_host, const float* x_s_host,
+                             float* y_host, int B, int L, int last_row_only, const tip_dropout* drop);
+int  tip_forward_host_wait(tip_model* m, int slot);
+
 /* ---- streaming (row a10: the window the runner rebuilds every frame) ------------------------- */
 /* Device-resident sliding windows for `n_streams` independent IMU streams
  * (replaces real_time_runner_minimal.py:131-147's per-frame re-assembly of the last <=40 rows).

@@ -180,6 +180,52 @@ def test_forward_host_pipelined_matches_device_call():
         assert np.abs(y_dev - ref).max() < TOL and np.abs(y_pageable - ref).max() < TOL
 
 
+def test_forward_host_job_pipeline():
+    """tip_forward_host_submit / _wait: several jobs in flight (uploads, forwards and downloads of different slots
+    overlap) give bit for bit what the device call gives for each batch, in submission order, through slot re-use
+    and graph replay; last_row_only, changing shapes and the pageable-buffer error."""
+    from tip_b200.pipeline import HostPipeline
+    sd = O.random_state_dict(32)
+    m = make_model(sd)
+    for B, L, depth in ((256, 40, 2), (5, 17, 3), (1, 40, 4)):
+        jobs = []
+        for j in range(7):
+            x_imu, x_s = O.synth_inputs(300 + j, B, L, nan_frac=0.1)
+            jobs.append((torch.from_numpy(x_imu).pin_memory(), torch.from_numpy(x_s).pin_memory(),
+                         torch.full((B, L, 131), float("nan")).pin_memory()))
+        want = [m(xi.cuda(), xs.cuda()).cpu().numpy() for xi, xs, _ in jobs]
+        pipe = HostPipeline(m, depth=depth)
+        done = []
+        for xi, xs, out in jobs:
+            r = pipe.submit(xi, xs, out)
+            if r is not None:
+                done.append(r)
+        assert len(pipe) == depth
+        done.extend(pipe.drain())
+        assert len(done) == len(jobs) and len(pipe) == 0
+        for (xi, xs, out), job, w in zip(done, jobs, want):
+            assert out is job[2]
+            np.testing.assert_array_equal(out.numpy(), w)
+        assert np.abs(want[0] - O.forward(sd, jobs[0][0].numpy(), jobs[0][1].numpy())).max() < TOL
+    # last row only
+    xi, xs, _ = jobs[0]
+    yl = torch.empty((1, 131)).pin_memory()
+    m.forward_host_submit(0, xi, xs, yl, last_row_only=True)
+    m.forward_host_wait(0)
+    m.forward_host_wait(0)                                           # idle slot: no-op
+    np.testing.assert_array_equal(yl.numpy(), want[0][:, -1])
+    # the blocking entry and the device call still work after the pipeline has drained
+    np.testing.assert_array_equal(m.forward_host(xi, xs).numpy(), want[0])
+    with pytest.raises(RuntimeError):
+        m.forward_host_submit(0, xi.clone(), xs, yl, last_row_only=True)      # pageable input
+    with pytest.raises(RuntimeError):
+        m.forward_host_submit(9, xi, xs, yl, last_row_only=True)              # no such slot
+    lib = capi.load_library()
+    pageable = torch.empty((1, 40, 131))
+    rc = lib.tip_forward_host_submit(m._handle, 0, xi.data_ptr(), xs.data_ptr(), pageable.data_ptr(), 1, 40, 0, None)
+    assert rc == 1 and b"page-locked" in lib.tip_last_error(m._handle)       # TIP_ERR_INVALID_ARG from the C side
+
+
 def test_repack_on_load_state_dict_and_param_update():
     sd_a, sd_b = O.random_state_dict(25), O.random_state_dict(26)
     m = make_model(sd_a)

@@ -90,6 +90,16 @@ struct tip_model {
     cudaStream_t s_in = nullptr, s_out = nullptr, s_part[2] = {nullptr, nullptr};
     cudaEvent_t ev_start = nullptr, ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     struct PartGraph { cudaGraphExec_t exec = nullptr; int B = 0, L = 0, w0 = 0, nw = 0, launches = 0, seen = 0; } part_graph[2];
+    // host entry, job pipeline (tip_forward_host_submit / _wait): per-slot device staging + completion events; one upload,
+    // one forward and one download stream shared by all slots (the forwards share the workspace, so they serialise)
+    struct HostSlot {
+        size_t cap = 0;           // rows
+        float *d_ximu = nullptr, *d_xs = nullptr, *d_y = nullptr;
+        cudaEvent_t ev_in = nullptr, ev_fwd = nullptr, ev_out = nullptr;
+        bool busy = false;
+        int launches = 0;
+    } hslot[TIP_HOST_SLOTS];
+    cudaStream_t hs_in = nullptr, hs_fwd = nullptr, hs_out = nullptr;
 
     // per-stage profiling (tip_set_profile)
     int profile = 0;
@@ -234,6 +244,11 @@ extern "C" void tip_destroy(tip_model* m) {
         cudaStreamDestroy(m->s_in); cudaStreamDestroy(m->s_out); cudaStreamDestroy(m->s_part[0]); cudaStreamDestroy(m->s_part[1]);
         cudaEventDestroy(m->ev_start);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_in[i]); cudaEventDestroy(m->ev_out[i]); }
+    }
+    if (m->hs_in) { cudaStreamDestroy(m->hs_in); cudaStreamDestroy(m->hs_fwd); cudaStreamDestroy(m->hs_out); }
+    for (auto& hsl : m->hslot) {
+        for (float* p : {hsl.d_ximu, hsl.d_xs, hsl.d_y}) if (p) cudaFree(p);
+        for (cudaEvent_t e : {hsl.ev_in, hsl.ev_fwd, hsl.ev_out}) if (e) cudaEventDestroy(e);
     }
     if (m->blob) cudaFree(m->blob);
     if (m->ws) cudaFree(m->ws);
@@ -964,6 +979,87 @@ extern "C" int tip_forward_host(tip_model* m, const float* x_imu_h, const float*
     TIP_CUDA_TRY(m, cudaMemcpyAsync(hdst, dsrc, out_rows * d.size_s * sizeof(float), cudaMemcpyDeviceToHost, st));
     TIP_CUDA_TRY(m, cudaStreamSynchronize(st));
     if (!out_pinned) memcpy(y_h, m->h_out, out_rows * d.size_s * sizeof(float));
+    return TIP_OK;
+}
+
+// ---- job pipeline over host buffers ----------------------------------------------------------------
+// tip_forward_host is one blocking call: upload (167 us at B = 256), forward (512 us), download (98 us) in sequence.  A
+// caller with many batches (the offline evaluator, a serving loop) does not need step i's result before it hands
+// over step i+1, so the three legs of consecutive jobs can overlap: uploads on hs_in, forwards (whole-batch graph
+// replays, serialised: they share the workspace) on hs_fwd, downloads on hs_out, each job with its own device staging.
+// In steady state the GPU runs forwards back to back and both PCIe directions are busy underneath them.
+extern "C" int tip_forward_host_wait(tip_model* m, int slot) {
+    if (!m) return TIP_ERR_INVALID_ARG;
+    if (slot < 0 || slot >= TIP_HOST_SLOTS) { m->set_error("tip_forward_host_wait: slot out of range"); return TIP_ERR_INVALID_ARG; }
+    tip_model::HostSlot& s = m->hslot[slot];
+    if (!s.busy) return TIP_OK;
+    TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    s.busy = false;
+    TIP_CUDA_TRY(m, cudaEventSynchronize(s.ev_out));
+    return TIP_OK;
+}
+
+extern "C" int tip_forward_host_submit(tip_model* m, int slot, const float* x_imu_h, const float* x_s_h, float* y_h,
+                                       int B, int L, int last_row_only, const tip_dropout* drop) {
+    if (!m) return TIP_ERR_INVALID_ARG;
+    if (slot < 0 || slot >= TIP_HOST_SLOTS || !x_imu_h || !x_s_h || !y_h || B < 1 || L < 1 || L > MAXL) {
+        m->set_error("tip_forward_host_submit: need 0 <= slot < TIP_HOST_SLOTS, non-null buffers, B >= 1 and 1 <= L <= 40");
+        return TIP_ERR_INVALID_ARG;
+    }
+    if (!m->packed) { m->set_error("tip_forward_host_submit before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
+    TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    if (!(is_pinned_host(x_imu_h) && is_pinned_host(x_s_h) && is_pinned_host(y_h))) {
+        // a pageable buffer would turn every cudaMemcpyAsync into a staged, host-blocking copy: no overlap, and the
+        // caller could not tell when its buffer is free again
+        m->set_error("tip_forward_host_submit: the three host buffers must be page-locked (cudaHostAlloc / cudaHostRegister / "
+                     "tensor.pin_memory()); use tip_forward_host for pageable memory");
+        return TIP_ERR_INVALID_ARG;
+    }
+    int rc = tip_forward_host_wait(m, slot);            // re-using a slot waits for its previous job
+    if (rc != TIP_OK) return rc;
+    const Dims& d = m->d;
+    tip_model::HostSlot& s = m->hslot[slot];
+    if (!m->hs_in) {
+        TIP_CUDA_TRY(m, cudaStreamCreateWithFlags(&m->hs_in, cudaStreamNonBlocking));
+        TIP_CUDA_TRY(m, cudaStreamCreateWithFlags(&m->hs_fwd, cudaStreamNonBlocking));
+        TIP_CUDA_TRY(m, cudaStreamCreateWithFlags(&m->hs_out, cudaStreamNonBlocking));
+    }
+    if (!s.ev_in) {
+        TIP_CUDA_TRY(m, cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+        TIP_CUDA_TRY(m, cudaEventCreateWithFlags(&s.ev_fwd, cudaEventDisableTiming));
+        TIP_CUDA_TRY(m, cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+    }
+    const size_t rows = (size_t)B * L;
+    if (rows > s.cap) {
+        for (float** p : {&s.d_ximu, &s.d_xs, &s.d_y}) if (*p) { cudaFree(*p); *p = nullptr; }
+        s.cap = 0;
+        const size_t cap = align_up(rows, 64);
+        TIP_CUDA_TRY(m, cudaMalloc(&s.d_ximu, cap * d.n_imu * sizeof(float)));
+        TIP_CUDA_TRY(m, cudaMalloc(&s.d_xs, cap * d.size_s * sizeof(float)));
+        TIP_CUDA_TRY(m, cudaMalloc(&s.d_y, cap * d.size_s * sizeof(float)));
+        s.cap = cap;
+    }
+    TIP_CUDA_TRY(m, cudaMemcpyAsync(s.d_ximu, x_imu_h, rows * d.n_imu * sizeof(float), cudaMemcpyHostToDevice, m->hs_in));
+    TIP_CUDA_TRY(m, cudaMemcpyAsync(s.d_xs, x_s_h, rows * d.size_s * sizeof(float), cudaMemcpyHostToDevice, m->hs_in));
+    TIP_CUDA_TRY(m, cudaEventRecord(s.ev_in, m->hs_in));
+    TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->hs_fwd, s.ev_in, 0));
+    // graph replay from the slot's third job on (tip_forward keys its captured forwards on the staging addresses)
+    rc = tip_forward(m, s.d_ximu, s.d_xs, s.d_y, B, L, nullptr, 1.f, drop, m->hs_fwd);
+    if (rc != TIP_OK) return rc;
+    const float* dsrc = s.d_y;
+    size_t out_rows = rows;
+    if (last_row_only) {
+        launch_k(last_row_kernel, dim3((B * d.size_s + 255) / 256), dim3(256), 0, m->hs_fwd, s.d_y, s.d_xs, B, L, d.size_s);
+        m->launches++;
+        dsrc = s.d_xs;
+        out_rows = (size_t)B;
+    }
+    s.launches = m->launches;
+    TIP_CUDA_TRY(m, cudaEventRecord(s.ev_fwd, m->hs_fwd));
+    TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->hs_out, s.ev_fwd, 0));
+    TIP_CUDA_TRY(m, cudaMemcpyAsync(y_h, dsrc, out_rows * d.size_s * sizeof(float), cudaMemcpyDeviceToHost, m->hs_out));
+    TIP_CUDA_TRY(m, cudaEventRecord(s.ev_out, m->hs_out));
+    s.busy = true;
     return TIP_OK;
 }
 

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libtip_b200.so")
 
 TIP_OK = 0
+TIP_HOST_SLOTS = 4          # job slots of tip_forward_host_submit / _wait
 STATUS_NAMES = {0: "TIP_OK", 1: "TIP_ERR_INVALID_ARG", 2: "TIP_ERR_NOT_PACKED", 3: "TIP_ERR_CUDA",
                 4: "TIP_ERR_NO_DEVICE", 5: "TIP_ERR_OOM"}
 
@@ -46,6 +47,9 @@ SIGNATURES = {
                               C.POINTER(TipDropout), _VP]),
     "tip_forward_host": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(TipDropout), _VP]),
+    "tip_forward_host_submit": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(TipDropout)]),
+    "tip_forward_host_wait": (C.c_int, [_VP, C.c_int]),
     "tip_stream_reset": (C.c_int, [_VP, C.c_int]),
     "tip_stream_step": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.POINTER(TipDropout), _VP]),
     "tip_stream_length": (C.c_int, [_VP]),

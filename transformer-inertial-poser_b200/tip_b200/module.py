@@ -272,6 +272,42 @@ class TF_RNN_Past_State(nn.Module):
         capi.check(self._lib, h, rc, "tip_forward_host")
         return y
 
+    def forward_host_submit(self, slot, x_imu, x_s, out, last_row_only=False):
+        """Queue one ``forward_host`` job in job slot ``slot`` (0..3) and return at once
+        (tip_forward_host_submit): upload, forward and download run on the handle's own streams and
+        overlap with the other slots' jobs.  All three tensors must be pinned, contiguous fp32 CPU
+        tensors and must not be touched until ``forward_host_wait(slot)`` returns."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("forward_host_submit: move the module to a CUDA device first (.cuda())")
+        h = self._ensure(dev, fast=True)
+        for name, t in (("x_imu", x_imu), ("x_s", x_s), ("out", out)):
+            if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() \
+                    or not t.is_pinned():
+                raise RuntimeError(f"forward_host_submit: {name} must be a pinned, contiguous fp32 CPU tensor "
+                                   "(tensor.pin_memory())")
+        if x_imu.dim() != 3 or x_s.dim() != 3 or x_imu.shape[:2] != x_s.shape[:2] or x_imu.shape[2] != self._n_imu \
+                or x_s.shape[2] != self._size_s:
+            raise RuntimeError(f"expected x_imu (B,L,{self._n_imu}) and x_s (B,L,{self._size_s}), "
+                               f"got {tuple(x_imu.shape)} and {tuple(x_s.shape)}")
+        B, L = x_imu.shape[0], x_imu.shape[1]
+        shape = (B, self._size_s) if last_row_only else (B, L, self._size_s)
+        if tuple(out.shape) != shape:
+            raise RuntimeError(f"forward_host_submit: out must have shape {shape}")
+        drop = self._dropout_struct()
+        with torch.cuda.device(dev):
+            rc = self._lib.tip_forward_host_submit(h, int(slot), x_imu.data_ptr(), x_s.data_ptr(), out.data_ptr(),
+                                                   B, L, int(last_row_only), C.byref(drop) if drop else None)
+        capi.check(self._lib, h, rc, "tip_forward_host_submit")
+
+    def forward_host_wait(self, slot):
+        """Block until the job in ``slot`` is complete (its ``out`` is filled); no-op for an idle slot."""
+        if self._handle is None:
+            return
+        with torch.cuda.device(self._device):
+            rc = self._lib.tip_forward_host_wait(self._handle, int(slot))
+        capi.check(self._lib, self._handle, rc, "tip_forward_host_wait")
+
     def set_gemm_engine(self, engine: int):
         """0 auto (= 2), 1 FFMA fp32 cross-check kernels, 2 tcgen05 3xFP16-split kernels (tip_set_gemm_engine)."""
         dev = next(self.parameters()).device
