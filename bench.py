@@ -16,6 +16,7 @@ import argparse
 import contextlib
 import io
 import json
+import math
 import os
 import sys
 import threading
@@ -189,7 +190,8 @@ def main():
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05 3xFP16 split")
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU-baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-depth", type=int, default=2, help="jobs in flight in the e2e leg's host pipeline (1..4)")
+    ap.add_argument("--lanes", type=int, default=3, help="execution lanes (concurrent whole-batch forwards)")
+    ap.add_argument("--e2e-depth", type=int, default=0, help="jobs in flight in the e2e leg's host pipeline (0: 2 per lane)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -216,14 +218,15 @@ def main():
     if args.engine:
         model.set_gemm_engine(args.engine)
 
-    # inputs: several distinct batches, resident in HBM (seed 1 at N=1; 100+rank for replicas)
-    n_sets = 4
+    # inputs: 16 distinct batches resident in HBM (seed 1 at N=1; 100+rank for replicas): 16 x 9.05 MB = 145 MB of
+    # inputs rotate through the timed region, more than the 126 MB L2, so no step finds its inputs cached
+    n_sets = 16
     base_seed = 1 if world == 1 else 100 + rank
     sets = []
     for i in range(n_sets):
         xi, xs = synth(base_seed + 1000 * i, B)
         sets.append((torch.from_numpy(xi).to(dev), torch.from_numpy(xs).to(dev)))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2 (single-lane leg)
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,34 +234,67 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 2 * n_sets)):       # every input set twice: its forward graph is captured on the 2nd call
-        model(*sets[i % n_sets])
+    # execution lanes: whole-batch forwards of consecutive steps run on `--lanes` handles (shared parameters, own
+    # workspace) on their own streams, so one step's narrow phases (LayerNorm GEMMs: 80 row tiles, recurrence: 104 SMs)
+    # are filled by its neighbours' kernels.  Every step is still one full forward of one batch of B windows.
+    from tip_b200.pipeline import ForwardLanes
+    NL = args.lanes
+    lanes = ForwardLanes(model, NL)
+    outs = [torch.empty((B, L_WIN, 131), dtype=torch.float32, device=dev) for _ in range(NL)]
+    if args.engine:
+        for lm in lanes.models[1:]:
+            lm.set_gemm_engine(args.engine)
+
+    def run_steps(k0, n):
+        lanes.fork()
+        for i in range(k0, k0 + n):
+            lanes.forward(i, *sets[i % n_sets], out=outs[i % NL])
+        lanes.join()
+
+    period = n_sets * NL // math.gcd(n_sets, NL)         # after `period` steps every (lane, input set) pair has been seen
+    run_steps(0, max(args.warmup, 3 * period))            # each pair's forward graph is captured on its 2nd sighting
     barrier()
 
-    # ---- timed region: K steps, per-step CUDA events on the launch stream, L2 flushed between --
+    # ---- timed region: K steps, ONE CUDA-event pair around them on the launch stream (the lane streams fork from /
+    #      join into it), barrier + synchronize on both sides --------------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.zero_()                                   # evict weights/inputs/activations from L2
-        ev[i][0].record()
-        model(*sets[i % n_sets])
-        ev[i][1].record()
-        launches += model.last_launch_count()
+    ev0.record()
+    run_steps(0, args.steps)
+    ev1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    sampler.stop_flag = True
-    sampler.join()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = sum(lanes.last_launch_count(i) for i in range(args.steps))
+    dev_ms = ev0.elapsed_time(ev1)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     ms_per_step = dev_ms / args.steps
     value = world * B * args.steps / (dev_ms / 1e3)
+
+    # ---- the same K steps one at a time on one lane, L2 flushed before each, per-step CUDA events: the latency of
+    #      ONE forward (what the roofline legs below are stated against) ------------------------------------------
+    for i in range(2 * n_sets):
+        model(*sets[i % n_sets], out=outs[0])
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()                                   # evict weights/inputs/activations from L2
+        ev[i][0].record()
+        model(*sets[i % n_sets], out=outs[0])
+        ev[i][1].record()
+    sampler.stop_flag = True
+    sampler.join()
+    barrier()
+    single_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    t = torch.tensor([single_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    single_ms = float(t.item())
 
     # ---- per-stage device times (roofline leg): a separate pass with an event before every kernel, same
     #      inputs, L2 flushed; outside the timed region because the per-kernel events perturb it ------------
@@ -279,7 +315,7 @@ def main():
     #      (b) job pipeline (the headline `e2e`): tip_forward_host_submit / _wait through HostPipeline, two
     #          jobs in flight, so step i+1's upload and step i-1's download run under step i's forward -------
     from tip_b200.pipeline import HostPipeline
-    DEPTH = args.e2e_depth
+    DEPTH = args.e2e_depth or 2 * NL
     NB = DEPTH + 1                          # buffer sets: a handed-back job's buffers are not those of the job just submitted
     hx = [(torch.from_numpy(synth(base_seed + 7000 + i, B)[0]).pin_memory(),
            torch.from_numpy(synth(base_seed + 7000 + i, B)[1]).pin_memory()) for i in range(NB)]
@@ -296,7 +332,7 @@ def main():
     e2e_check = float(y[0, -1, 0])          # the result is read on the host
     y_sync = [model.forward_host(hx[i][0], hx[i][1]).clone() for i in range(NB)]
 
-    pipe = HostPipeline(model, depth=DEPTH)
+    pipe = HostPipeline(model, depth=DEPTH, lanes=NL)
     for i in range(3 * NB):                 # each slot's forward graph is captured on its second job
         pipe.submit(hx[i % NB][0], hx[i % NB][1], hys[i % NB])
     for _ in pipe.drain():
@@ -425,11 +461,12 @@ def main():
         "3-product FP16 split (3 MMAs per product), so the reachable ceiling is peak/3",
         "us_per_launch": per_launch[dom] * 1e3, "share_of_step": totals[dom] / tot_stage if tot_stage else None,
         "stage_timing": "separate pass with a CUDA event before every kernel (graph replay off), L2 flushed; the events add "
-                        "~4 us per kernel, so the stage sum exceeds ms_per_step",
+                        "~4 us per kernel, so the stage sum exceeds single_lane.ms_per_step; kernels timed alone (one lane)",
         "stage_us_per_forward": {k: round(v * 1e3, 2) for k, v in sorted(totals.items(), key=lambda kv: -kv[1])},
         "kernels": kernels,
         "forward_hbm": {"bound": "hbm", "achieved": fwd_gbs, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": fwd_gbs / hbm_peak, "algorithmic_bytes": alg_bytes},
+                        "frac": fwd_gbs / hbm_peak, "algorithmic_bytes": alg_bytes,
+                        "note": "algorithmic bytes per step / ms_per_step (whole-job rate over all lanes)"},
         "forward_tensor": {"achieved": alg_flops / (ms_per_step * 1e-3) / 1e12, "peak": tf_peak,
                            "unit": "TFLOP/s", "frac": alg_flops / (ms_per_step * 1e-3) / 1e12 / tf_peak},
     }
@@ -448,9 +485,13 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": f"synthetic windows (SURVEY 8d distributions), {wdesc}",
         "config": {"workload": f"batch={B} synthetic IMU windows per GPU, seq_len=40, 6 IMUs, fp32, tf_layers=4 "
                                "nhid=1024 heads=16 (BASELINE configs[1]); replicas only",
-                   "l2": "256 MiB memset between timed steps (outside the per-step event pair) + 4 rotating input sets",
-                   "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks; each step is one "
-                             "forward, replayed as a CUDA graph (25 kernels, programmatic dependent launch)",
+                   "l2": f"inputs larger than L2: {n_sets} rotating device-resident input sets = "
+                         f"{n_sets * B * L_WIN * 221 * 4 / 1e6:.0f} MB > 126 MB (plus ~165 MB of activations per lane per step); "
+                         "the single_lane leg flushes L2 with a 256 MiB memset before every step",
+                   "timing": f"one CUDA-event pair on the launch stream around all K steps (lane streams fork from / join into it), "
+                             f"max over ranks; step i is one whole-batch forward on lane i % {NL} ({NL} handles sharing the "
+                             "parameters, own workspace and stream), each replayed as a CUDA graph (25 kernels)",
+                   "lanes": NL,
                    "engine": {0: "auto (tcgen05 3xFP16 split)", 1: "ffma", 2: "tcgen05-3xfp16"}[args.engine]},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -464,6 +505,9 @@ def main():
         "gpu_launches": launches,
         "roofline": roofline,
         "wall_s_timed_region": t_wall,
+        "single_lane": {"ms_per_step": single_ms, "value": world * B / (single_ms * 1e-3), "unit": UNIT,
+                        "what": "the same K steps one at a time on one lane, 256 MiB L2 flush before each, per-step CUDA events "
+                                "(latency of one forward; the per-kernel roofline table refers to this mode)"},
     }
     if stream_lat:
         out["stream_latency"] = stream_lat

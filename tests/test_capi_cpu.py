@@ -83,3 +83,70 @@ def test_attributes_and_no_cpu_fallback():
     x_imu, x_s = O.synth_inputs(0, 1, 4)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.from_numpy(x_imu), torch.from_numpy(x_s))
+
+
+def test_make_lane_shares_parameters_and_owns_nothing_else():
+    m = _make()
+    m.past_state_dropout = 0.0
+    lane = m.make_lane()
+    assert type(lane) is type(m) and lane._handle is None
+    assert list(lane.state_dict().keys()) == list(m.state_dict().keys())
+    for a, b in zip(lane.parameters(), m.parameters()):
+        assert a is b                                            # the same Parameter objects, not copies
+    assert lane.past_state_dropout == 0.0 and lane.n_heads == 16 and lane.training == m.training
+    m.train()
+    m.in_dropout = 0.3
+    lane._sync_lane_settings(m)
+    assert lane.training and lane.in_dropout == 0.3
+    norn = _make(with_rnn=False).make_lane()
+    assert norn.rnn is None and "rnn.weight_hh_l0" not in norn.state_dict()
+
+
+def test_host_pipeline_slot_rotation_and_order():
+    """Host logic of HostPipeline with a recording stand-in for the module: jobs come back in submission order,
+    never more than `depth` in flight, a (lane, slot) pair is never re-used while its job is in flight."""
+    from tip_b200.pipeline import HostPipeline
+
+    class Rec:
+        def __init__(self, log, name="L0"):
+            self.log, self.name, self.n = log, name, 0
+            self.in_dropout = self.past_state_dropout = 0.0
+            self.training = False
+
+        def make_lane(self):
+            self.n += 1
+            return Rec(self.log, f"L{self.n}")
+
+        def _sync_lane_settings(self, src):
+            pass
+
+        def forward_host_submit(self, slot, xi, xs, out, last_row_only=False):
+            self.log.append(("submit", self.name, slot, out))
+
+        def forward_host_wait(self, slot):
+            self.log.append(("wait", self.name, slot))
+
+    for depth, lanes in ((1, 1), (2, 1), (4, 1), (4, 2), (6, 3), (5, 2)):
+        log = []
+        pipe = HostPipeline(Rec(log), depth=depth, lanes=lanes)
+        got = []
+        for j in range(23):
+            r = pipe.submit("xi", "xs", j)
+            assert len(pipe) <= depth
+            if r is not None:
+                got.append(r[2])
+        got += [r[2] for r in pipe.drain()]
+        assert got == list(range(23))
+        busy = {}
+        for e in log:
+            if e[0] == "submit":
+                assert (e[1], e[2]) not in busy, (depth, lanes, e)
+                busy[(e[1], e[2])] = e[3]
+            else:
+                busy.pop((e[1], e[2]))
+        assert not busy
+        assert {e[1] for e in log} == {f"L{i}" for i in range(lanes)}
+    with pytest.raises(ValueError):
+        HostPipeline(Rec([]), depth=5, lanes=1)
+    with pytest.raises(ValueError):
+        HostPipeline(Rec([]), depth=0)

@@ -226,6 +226,51 @@ def test_forward_host_job_pipeline():
     assert rc == 1 and b"page-locked" in lib.tip_last_error(m._handle)       # TIP_ERR_INVALID_ARG from the C side
 
 
+def test_execution_lanes():
+    """make_lane(): shared parameters, own handle.  Forwards of different lanes running concurrently on their own
+    streams give bit for bit the single-lane results (ForwardLanes with device tensors, HostPipeline with host
+    buffers spread over lanes), and a parameter update through the owner reaches every lane."""
+    from tip_b200.pipeline import ForwardLanes, HostPipeline
+    sd = O.random_state_dict(33)
+    m = make_model(sd)
+    B, L = 256, 40
+    sets = []
+    for j in range(5):
+        x_imu, x_s = O.synth_inputs(400 + j, B, L, nan_frac=0.05)
+        sets.append((torch.from_numpy(x_imu).cuda(), torch.from_numpy(x_s).cuda()))
+    want = [m(*s).clone() for s in sets]
+    lanes = ForwardLanes(m, 3)
+    assert len(lanes) == 3 and lanes.models[1].linear.weight is m.linear.weight
+    for rep in range(3):                                       # eager, captured, replayed
+        outs = [torch.empty((B, L, 131), device="cuda") for _ in sets]
+        lanes.fork()
+        for k, s in enumerate(sets):
+            lanes.forward(k, *s, out=outs[k])
+        lanes.join()
+        torch.cuda.synchronize()
+        for o, w in zip(outs, want):
+            assert torch.equal(o, w)
+    # host buffers over two lanes
+    jobs = [(s[0].cpu().pin_memory(), s[1].cpu().pin_memory(), torch.empty((B, L, 131)).pin_memory()) for s in sets]
+    pipe = HostPipeline(m, depth=4, lanes=2)
+    done = [r for j in jobs + jobs if (r := pipe.submit(*j)) is not None]
+    done += list(pipe.drain())
+    assert len(done) == 2 * len(jobs)
+    for k, (xi, xs, out) in enumerate(done):
+        assert out is jobs[k % len(jobs)][2] and torch.equal(out, want[k % len(jobs)].cpu())
+    # a parameter update is seen by every lane (version counters of the shared Parameters)
+    with torch.no_grad():
+        m.linear.bias.add_(1.0)
+    lanes.fork()
+    ys = [lanes.forward(k, *sets[0]) for k in range(3)]
+    lanes.join()
+    torch.cuda.synchronize()
+    for y in ys:
+        assert float((y - (want[0] + 1.0)).abs().max()) < 1e-5
+    with pytest.raises(ValueError):
+        HostPipeline(m, depth=9, lanes=2)
+
+
 def test_repack_on_load_state_dict_and_param_update():
     sd_a, sd_b = O.random_state_dict(25), O.random_state_dict(26)
     m = make_model(sd_a)

@@ -39,7 +39,7 @@ struct FwdGraph {
     int launches = 0;
     uint64_t last_use = 0;
 };
-constexpr int FWD_GRAPH_SLOTS = 8;
+constexpr int FWD_GRAPH_SLOTS = 32;     // captured forwards kept per handle (LRU); a lane rotating 16 input sets needs 16
 
 struct tip_model {
     tip_dims cdims{};

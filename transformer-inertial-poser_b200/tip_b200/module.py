@@ -210,15 +210,23 @@ class TF_RNN_Past_State(nn.Module):
         return (x_imu.detach().to(torch.float32).contiguous(),
                 x_s.detach().to(torch.float32).contiguous())
 
-    def forward(self, x_imu, x_s, keep_mask=None, past_scale=1.0):
+    def forward(self, x_imu, x_s, keep_mask=None, past_scale=1.0, out=None):
         """(B, L, 72|90), (B, L, size_s) -> (B, L, size_s); reference :60-102.  Inputs are not
         modified.  ``keep_mask`` (test hook): explicit 0/1 mask used instead of drawing the
-        past-state dropout mask; x_s is multiplied by keep_mask * past_scale."""
+        past-state dropout mask; x_s is multiplied by keep_mask * past_scale.  ``out`` (beyond the
+        reference surface): pre-allocated contiguous fp32 CUDA tensor of the result's shape; with stable
+        input / output addresses a repeated forward is one CUDA-graph replay."""
         x_imu, x_s = self._check_inputs(x_imu, x_s)
         dev = x_imu.device
         h = self._ensure(dev)
         B, L = x_imu.shape[0], x_imu.shape[1]
-        y = torch.empty((B, L, self._size_s), dtype=torch.float32, device=dev)
+        if out is None:
+            y = torch.empty((B, L, self._size_s), dtype=torch.float32, device=dev)
+        else:
+            y = out
+            if y.device != dev or y.dtype != torch.float32 or tuple(y.shape) != (B, L, self._size_s) \
+                    or not y.is_contiguous():
+                raise RuntimeError(f"out must be a contiguous fp32 tensor of shape {(B, L, self._size_s)} on {dev}")
         if B == 0:
             return y
         drop = self._dropout_struct()
@@ -237,6 +245,31 @@ class TF_RNN_Past_State(nn.Module):
         return y
 
     # ---- extras beyond the reference surface --------------------------------------------------
+    def make_lane(self):
+        """A second execution lane: a module that SHARES this module's Parameter objects (no copy; a
+        ``load_state_dict`` / optimiser step / ``.cuda()`` on either is seen by both) but owns its own C
+        handle, i.e. its own packed weights, workspace, captured graphs and job slots.  Forwards of
+        different lanes may run concurrently on different CUDA streams -- the LayerNorm GEMMs (80 row
+        tiles at B = 256) and the recurrence (104 SMs) leave SMs idle that another lane's kernels fill:
+        two lanes give 598 k instead of 498 k frames/s at B = 256.  Dropout settings and train/eval mode
+        are copied at creation (``ForwardLanes`` / ``HostPipeline`` refresh them on every call)."""
+        lane = object.__new__(type(self))
+        nn.Module.__init__(lane)
+        for name, child in self._modules.items():
+            lane._modules[name] = child
+        for k in ("with_rnn", "rnn_hid_size", "in_dropout", "n_heads", "past_state_dropout", "_dims",
+                  "_size_s", "_n_imu"):
+            setattr(lane, k, getattr(self, k))
+        if "rnn" not in self._modules:
+            lane.rnn = None
+        lane.training = self.training
+        lane._lib = self._lib
+        lane._handle = lane._device = lane._packed_sig = lane._packed_versions = lane._plist = None
+        return lane
+
+    def _sync_lane_settings(self, src):
+        self.in_dropout, self.past_state_dropout, self.training = src.in_dropout, src.past_state_dropout, src.training
+
     def forward_host(self, x_imu, x_s, last_row_only=False, out=None):
         """``model(x_imu.cuda(), x_s.cuda()).cpu()`` in one C call with host (numpy / CPU tensor)
         buffers: H2D, forward, D2H, stream sync (real_time_runner_minimal.py:149).  Runs on the
@@ -280,7 +313,7 @@ class TF_RNN_Past_State(nn.Module):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("forward_host_submit: move the module to a CUDA device first (.cuda())")
-        h = self._ensure(dev, fast=True)
+        h = self._ensure(dev)          # full signature check: a lane does not see the owner's _apply
         for name, t in (("x_imu", x_imu), ("x_s", x_s), ("out", out)):
             if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() \
                     or not t.is_pinned():
