@@ -119,8 +119,11 @@ int  tip_forward_host(tip_model* m, const float* x_imu_host, const float* x_s_ho
  * once; uploads, forwards and downloads of different slots overlap (forwards themselves run one
  * after another: they share the workspace).  wait(slot) blocks until y_host of that slot's job is
  * complete; submitting to a busy slot waits for it first.  The three host buffers MUST be
- * page-locked (TIP_ERR_INVALID_ARG otherwise) and must stay untouched until wait returns.  Until
- * every submitted slot has been waited for, no other entry point may be called on this handle. */
+ * page-locked (TIP_ERR_INVALID_ARG otherwise) and must stay untouched until wait returns.  The
+ * jobs share the handle's workspace with every other entry point: tip_forward / tip_forward_host /
+ * tip_stream_* / tip_pack_weights on the same handle first wait (host side) for the submitted
+ * jobs' forwards, and a job submitted after a tip_forward on a caller stream runs after it.  For
+ * forwards that overlap each other use one handle per lane (the Python side: make_lane()). */
 #define TIP_HOST_SLOTS 4
 int  tip_forward_host_submit(tip_model* m, int slot, const float* x_imu_host, const float* x_s_host,
                              float* y_host, int B, int L, int last_row_only, const tip_dropout* drop);

@@ -216,6 +216,19 @@ def test_forward_host_job_pipeline():
     np.testing.assert_array_equal(yl.numpy(), want[0][:, -1])
     # the blocking entry and the device call still work after the pipeline has drained
     np.testing.assert_array_equal(m.forward_host(xi, xs).numpy(), want[0])
+    # other entry points while jobs are in flight are ordered against the pipeline (one workspace per handle)
+    for _, _, o in jobs:
+        o.fill_(float("nan"))
+    pipe = HostPipeline(m, depth=2)
+    pipe.submit(*jobs[1])
+    y_dev = m(jobs[2][0].cuda(), jobs[2][1].cuda())                  # waits for job 1's forward
+    pipe.submit(*jobs[3])                                            # runs after the device call
+    y_host = m.forward_host(jobs[4][0], jobs[4][1]).numpy()
+    list(pipe.drain())
+    np.testing.assert_array_equal(jobs[1][2].numpy(), want[1])
+    np.testing.assert_array_equal(y_dev.cpu().numpy(), want[2])
+    np.testing.assert_array_equal(jobs[3][2].numpy(), want[3])
+    np.testing.assert_array_equal(y_host, want[4])
     with pytest.raises(RuntimeError):
         m.forward_host_submit(0, xi.clone(), xs, yl, last_row_only=True)      # pageable input
     with pytest.raises(RuntimeError):

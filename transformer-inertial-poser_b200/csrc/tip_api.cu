@@ -100,6 +100,8 @@ struct tip_model {
         int launches = 0;
     } hslot[TIP_HOST_SLOTS];
     cudaStream_t hs_in = nullptr, hs_fwd = nullptr, hs_out = nullptr;
+    cudaEvent_t ev_user = nullptr;      // last forward a caller queued on its own stream (the pipeline's forwards wait for it)
+    bool ev_user_set = false;
 
     // per-stage profiling (tip_set_profile)
     int profile = 0;
@@ -124,6 +126,8 @@ static void mark(tip_model* m, cudaStream_t st, const char* name, int layer = -1
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int quiesce_host_jobs(tip_model* m);      // wait until no pipelined host job still uses the workspace / weights
 
 // every captured graph bakes in workspace addresses, tensor maps and the engine choice
 static void drop_graphs(tip_model* m) {
@@ -245,7 +249,8 @@ extern "C" void tip_destroy(tip_model* m) {
         cudaEventDestroy(m->ev_start);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_in[i]); cudaEventDestroy(m->ev_out[i]); }
     }
-    if (m->hs_in) { cudaStreamDestroy(m->hs_in); cudaStreamDestroy(m->hs_fwd); cudaStreamDestroy(m->hs_out); }
+    for (auto& hsl : m->hslot) if (hsl.busy) cudaEventSynchronize(hsl.ev_out);
+    if (m->hs_in) { cudaStreamDestroy(m->hs_in); cudaStreamDestroy(m->hs_fwd); cudaStreamDestroy(m->hs_out); cudaEventDestroy(m->ev_user); }
     for (auto& hsl : m->hslot) {
         for (float* p : {hsl.d_ximu, hsl.d_xs, hsl.d_y}) if (p) cudaFree(p);
         for (cudaEvent_t e : {hsl.ev_in, hsl.ev_fwd, hsl.ev_out}) if (e) cudaEventDestroy(e);
@@ -267,6 +272,7 @@ extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64
     cudaStream_t st = (cudaStream_t)stream_;
     const Dims& d = m->d;
     if (n != tip_num_weight_tensors(m)) { m->set_error("wrong number of weight tensors"); return TIP_ERR_INVALID_ARG; }
+    { const int qrc = quiesce_host_jobs(m); if (qrc != TIP_OK) return qrc; }
     // expected element counts in state-dict order
     std::vector<int64_t> exp;
     exp.push_back((int64_t)E * d.d_in); exp.push_back(E);
@@ -759,8 +765,38 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
     return TIP_OK;
 }
 
+// The job pipeline's forwards (tip_forward_host_submit, stream hs_fwd) and forwards a caller queues on its own stream
+// share the handle's workspace.  Entry points that are not part of the pipeline first wait (host side) until no
+// submitted job still needs the workspace; the pipeline's next forward waits (device side) for the caller's last one.
+static int quiesce_host_jobs(tip_model* m) {
+    for (auto& s : m->hslot)
+        if (s.busy) TIP_CUDA_TRY(m, cudaEventSynchronize(s.ev_fwd));
+    return TIP_OK;
+}
+
+static int forward_impl(tip_model* m, const float* x_imu, const float* x_s, float* y, int B, int L,
+                        const float* keep_mask, float past_scale, const tip_dropout* drop, void* stream_);
+
 extern "C" int tip_forward(tip_model* m, const float* x_imu, const float* x_s, float* y, int B, int L,
                            const float* keep_mask, float past_scale, const tip_dropout* drop, void* stream_) {
+    if (!m) return TIP_ERR_INVALID_ARG;
+    if (!m->hs_fwd) return forward_impl(m, x_imu, x_s, y, B, L, keep_mask, past_scale, drop, stream_);
+    // the job pipeline has been used on this handle: order this forward against it
+    int rc = quiesce_host_jobs(m);
+    if (rc != TIP_OK) return rc;
+    rc = forward_impl(m, x_imu, x_s, y, B, L, keep_mask, past_scale, drop, stream_);
+    if (rc != TIP_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream_;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+        TIP_CUDA_TRY(m, cudaEventRecord(m->ev_user, st));
+        m->ev_user_set = true;
+    }
+    return TIP_OK;
+}
+
+static int forward_impl(tip_model* m, const float* x_imu, const float* x_s, float* y, int B, int L,
+                        const float* keep_mask, float past_scale, const tip_dropout* drop, void* stream_) {
     if (!m) return TIP_ERR_INVALID_ARG;
     if (!m->packed) { m->set_error("tip_forward before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
     if (!x_imu || !x_s || !y || B < 1 || L < 1 || L > MAXL) {
@@ -889,6 +925,7 @@ extern "C" int tip_forward_host(tip_model* m, const float* x_imu_h, const float*
     if (!m->packed) { m->set_error("tip_forward_host before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
     cudaStream_t st = (cudaStream_t)stream_;
     TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    { const int qrc = quiesce_host_jobs(m); if (qrc != TIP_OK) return qrc; }
     const Dims& d = m->d;
     const size_t rows = (size_t)B * L;
     if (rows > m->host_cap) {
@@ -1023,6 +1060,8 @@ extern "C" int tip_forward_host_submit(tip_model* m, int slot, const float* x_im
         TIP_CUDA_TRY(m, cudaStreamCreateWithFlags(&m->hs_in, cudaStreamNonBlocking));
         TIP_CUDA_TRY(m, cudaStreamCreateWithFlags(&m->hs_fwd, cudaStreamNonBlocking));
         TIP_CUDA_TRY(m, cudaStreamCreateWithFlags(&m->hs_out, cudaStreamNonBlocking));
+        TIP_CUDA_TRY(m, cudaEventCreateWithFlags(&m->ev_user, cudaEventDisableTiming));
+        TIP_CUDA_TRY(m, cudaDeviceSynchronize());      // once: forwards queued on caller streams before the pipeline existed
     }
     if (!s.ev_in) {
         TIP_CUDA_TRY(m, cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
@@ -1043,8 +1082,9 @@ extern "C" int tip_forward_host_submit(tip_model* m, int slot, const float* x_im
     TIP_CUDA_TRY(m, cudaMemcpyAsync(s.d_xs, x_s_h, rows * d.size_s * sizeof(float), cudaMemcpyHostToDevice, m->hs_in));
     TIP_CUDA_TRY(m, cudaEventRecord(s.ev_in, m->hs_in));
     TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->hs_fwd, s.ev_in, 0));
-    // graph replay from the slot's third job on (tip_forward keys its captured forwards on the staging addresses)
-    rc = tip_forward(m, s.d_ximu, s.d_xs, s.d_y, B, L, nullptr, 1.f, drop, m->hs_fwd);
+    if (m->ev_user_set) { TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->hs_fwd, m->ev_user, 0)); m->ev_user_set = false; }
+    // graph replay from the slot's third job on (the captured forwards are keyed on the staging addresses)
+    rc = forward_impl(m, s.d_ximu, s.d_xs, s.d_y, B, L, nullptr, 1.f, drop, m->hs_fwd);
     if (rc != TIP_OK) return rc;
     const float* dsrc = s.d_y;
     size_t out_rows = rows;
