@@ -190,6 +190,9 @@ def main():
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 FFMA, 2 tcgen05 3xFP16 split")
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU-baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-run", action="store_true",
+                    help="for ncu launch lists: exactly W warm-up steps (forwards stay eager until a graph is captured), "
+                         "no streaming / CPU-baseline legs")
     ap.add_argument("--lanes", type=int, default=3, help="execution lanes (concurrent whole-batch forwards)")
     ap.add_argument("--e2e-depth", type=int, default=0, help="jobs in flight in the e2e leg's host pipeline (0: 2 per lane)")
     args = ap.parse_args()
@@ -252,7 +255,8 @@ def main():
         lanes.join()
 
     period = n_sets * NL // math.gcd(n_sets, NL)         # after `period` steps every (lane, input set) pair has been seen
-    run_steps(0, max(args.warmup, 3 * period))            # each pair's forward graph is captured on its 2nd sighting
+    # each pair's forward graph is captured on its 2nd sighting
+    run_steps(0, args.warmup if args.profile_run else max(args.warmup, 3 * period))
     barrier()
 
     # ---- timed region: K steps, ONE CUDA-event pair around them on the launch stream (the lane streams fork from /
@@ -278,7 +282,7 @@ def main():
 
     # ---- the same K steps one at a time on one lane, L2 flushed before each, per-step CUDA events: the latency of
     #      ONE forward (what the roofline legs below are stated against) ------------------------------------------
-    for i in range(2 * n_sets):
+    for i in range(2 if args.profile_run else 2 * n_sets):
         model(*sets[i % n_sets], out=outs[0])
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -359,7 +363,7 @@ def main():
     # ---- BASELINE configs[2]: one stream, frame-by-frame (B=1, L ramps 1..40 then slides), host rows in,
     #      last output row back, closed loop; p50 / p99 per-frame latency of the public streaming call
     stream_lat = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.profile_run:
         from tip_b200.streaming import StreamSession
         sess = StreamSession(model, n_streams=1)
         xi, xs = synth(2, 1)
@@ -472,7 +476,7 @@ def main():
     }
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.profile_run:
         threads = os.cpu_count() or 1
         rate, n, el = cpu_port_rate(sd, B, args.cpu_budget, threads)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
