@@ -415,6 +415,21 @@ def test_batch_sizes_across_kernel_switch_points(engine):
         assert np.isfinite(y).all() and err < TOL, (B, err)
 
 
+def test_head_variants_at_batch_sizes():
+    """Both head variants (after the RNN, K = 512; without RNN, K = 256) and both size_s the reference ships, at
+    15-18 row tiles with ragged last tiles (the head's second 128-column tile holds size_s - 128 live columns)."""
+    for kw in (dict(), dict(size_s=119), dict(with_rnn=False)):
+        sd = O.random_state_dict(34, **kw)
+        m = make_model(sd, **kw)
+        for B, L in ((52, 40), (48, 40), (200, 11)):
+            x_imu, x_s = O.synth_inputs(500 + B, B, L, nan_frac=0.1, size_s=kw.get("size_s", 131),
+                                        with_acc_sum=True)
+            y = run(m, x_imu, x_s)
+            ref = O.forward(sd, x_imu, x_s, with_rnn=kw.get("with_rnn", True))
+            assert y.shape == ref.shape and np.isfinite(y).all()
+            assert np.abs(y - ref).max() < TOL, (kw, B, L, np.abs(y - ref).max())
+
+
 def test_graph_replay_reads_fresh_data():
     """A forward on the same buffers is replayed from a CUDA graph from the third call on; the replay must see the
     buffers' current contents, and switching graphs off must give the same numbers."""
