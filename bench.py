@@ -209,15 +209,23 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-
     sd, wdesc = load_weights()
     model = build_model(sd, dev)
     if world > 1:
-        from tip_b200.replicas import broadcast_weights
-        broadcast_weights(model, src=0)          # the ONE collective: weights at init over NVLink
+        # NCCL prints its version banner on stdout when the communicator is created: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            from tip_b200.replicas import broadcast_weights
+            broadcast_weights(model, src=0)          # the ONE collective: weights at init over NVLink
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     if args.engine:
         model.set_gemm_engine(args.engine)
 
