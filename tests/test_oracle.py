@@ -117,3 +117,34 @@ def test_product_synthetic_generators_match_the_oracle_copies():
         sa, sb = O.random_state_dict(4, **kw), S.random_state_dict(4, **kw)
         assert list(sa) == list(sb) and all(np.array_equal(sa[k], sb[k]) for k in sa)
     assert S.state_dict_keys() == O.state_dict_keys()
+
+
+def test_bench_reference_arm_runs_on_cpu_and_prints_one_json_line():
+    """`bench.py --impl reference` (the driver's reference arm) needs no GPU: one JSON line on stdout with the
+    contract's keys, timed on the CPU torch port."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--batch", "8"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "imu_frames_per_sec_seq40_6imu" and j["unit"] == "frames/s"
+    assert j["higher_is_better"] is True and j["value"] > 0 and j["n_gpus"] == 1
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_bench_reference_arm_only_rank0_works_under_torchrun_env():
+    """Launched under torchrun (N > 1) rank 0 alone runs the reference arm; the other ranks exit 0 silently."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "1", "--batch", "8"], capture_output=True, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == "", (r.stdout, r.stderr[-1000:])
