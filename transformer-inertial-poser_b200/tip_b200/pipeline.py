@@ -59,8 +59,12 @@ class ForwardLanes:
         m = self.models[i]
         if m is not self.model:
             m._sync_lane_settings(self.model)
+        caller = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.streams[i]):
-            return m(x_imu, x_s, out=out)
+            y = m(x_imu, x_s, out=out)
+        if out is None:
+            y.record_stream(caller)      # allocated on the lane's stream, consumed (after join()) on the caller's
+        return y
 
     def join(self):
         """The current stream waits for every lane."""
