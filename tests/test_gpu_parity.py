@@ -448,3 +448,21 @@ def test_graph_replay_reads_fresh_data():
         y2 = m(xi, xs).cpu().numpy()
         m.set_use_graphs(True)
         np.testing.assert_array_equal(y, y2)
+
+
+def test_b256_released_checkpoint_golden():
+    """BASELINE configs[1] exactly as the bench runs it: batch = 256, L = 40, the released checkpoint; golden
+    sub-sample, last rows of every window and checksum from the reference module (oracle/make_golden_ck_b256.py)."""
+    g = np.load(os.path.join(GOLD, "ck_b256_l40_sub.npz"))
+    sd = load_checkpoint(str(g["checkpoint"]))
+    if sd is None:
+        pytest.skip("baseline/_ref checkpoint not staged")
+    x_imu, x_s = O.synth_inputs(int(g["xseed"]), 256, 40)
+    m = make_model(sd)
+    y = run(m, x_imu, x_s)
+    assert np.isfinite(y).all()
+    assert np.abs(y[g["idx"]] - g["y_sub"]).max() < TOL
+    assert np.abs(y[:, -1] - g["y_last"]).max() < TOL
+    # relative checksum (outputs reach |y| = 11 with these weights): mean signed error per element below 1e-6
+    assert abs(y.astype(np.float64).sum() - float(g["y_sum"])) < 1e-6 * y.size + 0.5
+

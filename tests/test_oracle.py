@@ -60,6 +60,19 @@ def test_oracle_b256_subsample():
     assert abs(y.astype(np.float64).sum() - float(g["y_sum"])) < 1e-2
 
 
+def test_oracle_b256_subsample_released_checkpoint():
+    """BASELINE configs[1] with the released weights the bench uses (golden minted by oracle/make_golden_ck_b256.py)."""
+    g = np.load(os.path.join(GOLD, "ck_b256_l40_sub.npz"))
+    sd = load_checkpoint(str(g["checkpoint"]))
+    if sd is None:
+        pytest.skip("baseline/_ref checkpoint not staged")
+    x_imu, x_s = O.synth_inputs(int(g["xseed"]), 256, 40)
+    idx = g["idx"]
+    y = O.forward(sd, x_imu[idx], x_s[idx])
+    assert np.abs(y - g["y_sub"]).max() < TOL
+    assert np.abs(y[:, -1] - g["y_last"][idx]).max() < TOL
+
+
 def test_oracle_inputs_not_mutated_and_nan_handled():
     sd = O.random_state_dict(11)
     x_imu, x_s = O.synth_inputs(9, 2, 12, nan_frac=0.5)
