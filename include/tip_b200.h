@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TIP_ABI_VERSION 1
+#define TIP_ABI_VERSION 2
 
 typedef enum tip_status {
     TIP_OK = 0,
@@ -45,7 +45,7 @@ typedef enum tip_status {
  * (/root/reference/simple_transformer_with_state.py:9-17).  The kernels are specialised for the
  * one architecture the reference ships and constructs (offline_testing_simple.py:87-95,
  * live_demo_new.py:202-210): tf_in_dim=256, n_heads=16, tf_hid_size=1024, rnn_hid_size=512,
- * tf_layers<=8; input_size_imu=72, size_s<=160, with_rnn and with_acc_sum free.
+ * tf_layers<=8; input_size_imu=72, 111<=size_s<=144, with_rnn and with_acc_sum free.
  * Anything else makes tip_create return TIP_ERR_INVALID_ARG. */
 typedef struct tip_dims {
     int32_t input_size_imu;   /* 72 = 6 IMUs x (9 rotation + 3 acceleration) */
@@ -68,6 +68,17 @@ typedef struct tip_dropout {
     float    encoder_dropout;     /* p inside the encoder  (0.1 when the module is in train(), else 0) */
     uint64_t seed;                /* counter-based RNG seed for this call (ignored when all p are 0) */
 } tip_dropout;
+/* The masks are a pure function of (seed, dropout site, element index): one 64-bit splitmix hash gives four
+ * 16-bit uniforms, element idx is dropped when lane (idx & 3) of hash(seed + site, idx >> 2) < round(p * 65536),
+ * kept elements are scaled by 1/(1-p).  Sites and element indices (rows are b*L + t, batch-global):
+ *   x_imu (:73)  site 0x1111, idx = row * kin_pad + c            (c = column of the concatenated input row,
+ *   x_s   (:77)  site 0x2222, idx = row * kin_pad + n_imu + c     kin_pad = (n_imu + size_s) rounded up to 64)
+ *   layer l (0-based): attention probabilities 101*(l+1), idx = ((b*16 + h)*40 + query)*40 + key;
+ *   dropout1 (on out_proj, before the residual) 211*(l+1), idx = row*256 + col;  FFN inner dropout (after ReLU)
+ *   307*(l+1), idx = row*1024 + col;  dropout2 (on linear2) 401*(l+1), idx = row*256 + col.
+ * Batches of more than 1024 windows are processed in chunks of 1024; chunk k adds k * 0x632BE59BD9B4E019 to the
+ * seed and its rows / windows restart at 0.  oracle/tip_oracle.py restates the generator, so the stochastic mode
+ * is parity-tested mask for mask.  The seed is kept in device memory: stochastic forwards replay from CUDA graphs. */
 
 typedef struct tip_model tip_model;   /* opaque */
 
@@ -76,6 +87,13 @@ int  tip_abi_version(void);
 /* Mirrors TF_RNN_Past_State.__init__ (:9-54). Binds to the current CUDA device. */
 int  tip_create(const tip_dims* dims, tip_model** out);
 void tip_destroy(tip_model* m);
+/* An execution lane: a second handle on the owner's device that SHARES the owner's packed weights (no copy, no
+ * second pack) and owns everything else (workspace, tensor maps, captured graphs, job slots, seed).  Forwards of
+ * different handles may overlap on different streams -- one forward at a time leaves SMs idle in its narrow
+ * phases.  tip_pack_weights is called on the owner only; it waits for the lanes' in-flight forwards, and every
+ * lane orders its next forward after the pack.  The weights live until the last handle sharing them is destroyed.
+ * (The reference has no counterpart: it runs one blocking call at a time, offline_testing_simple.py:360-399.) */
+int  tip_create_lane(tip_model* owner, tip_model** out);
 const char* tip_last_error(const tip_model* m);   /* m may be NULL: last error of tip_create */
 
 /* ---- weights -------------------------------------------------------------------------------- */
@@ -87,12 +105,11 @@ int  tip_num_weight_tensors(const tip_model* m);
  * shapes), and builds the private packed copy (head-permutation folded into in_linear rows,
  * root-velocity columns zeroed, 1/sqrt(d) folded into W_q/b_q, RNN biases pre-summed, FP16
  * hi/lo splits).  Asynchronous on `stream`; the source tensors may be freed after the stream
- * has passed this point. */
+ * has passed this point.  Forwards queued later on ANY stream of this handle or its lanes run after the
+ * pack (event); when lanes or the handle's internal streams exist, the call first waits for the device to
+ * go idle (their in-flight forwards still read the old weights). */
 int  tip_pack_weights(tip_model* m, const float* const* tensors_dev, const int64_t* numels,
                       int n_tensors, void* stream);
-/* Packed weight blob (for the one-off NCCL broadcast of the replica launcher). */
-int  tip_packed_blob(tip_model* m, void** blob_dev, size_t* bytes);
-int  tip_mark_packed(tip_model* m);   /* after the blob was filled by a broadcast */
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 /* Mirrors TF_RNN_Past_State.forward (:60-102):

@@ -8,7 +8,7 @@ What runs unmodified from ``/root/reference``: ``real_time_runner_minimal.RTRunn
 state machine, :20-200), ``data_utils`` (rotation representations, root-local IMU rotation, SBP root
 correction), ``bullet_agent.SimAgent`` / ``bullet_utils`` / ``bullet_client``, ``amass_char_info``,
 ``constants`` and the model ``simple_transformer_with_state.TF_RNN_Past_State`` with the released
-checkpoint.  What is substituted (``oracle/shims``): ``fairmotion`` (numpy/scipy restatement of the few
+checkpoint.  What is substituted (``tools/ref_env/shims``): ``fairmotion`` (numpy/scipy restatement of the few
 conversions used) and ``pybullet`` (kinematic FK over ``data/amass.urdf``) -- neither is installed here.
 Two process-level adaptations, both outside the reference sources:
   * ``torch.Tensor.cuda`` is made the identity (the runner hard-codes ``.cuda()`` at :149; this container
@@ -29,7 +29,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
-SHIMS = os.path.join(ROOT, "oracle", "shims")
+SHIMS = os.path.join(ROOT, "tools", "ref_env", "shims")
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 

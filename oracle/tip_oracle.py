@@ -113,9 +113,58 @@ def _layer_norm(x, w, b, eps=1e-5):
     return xc / np.sqrt(var + x.dtype.type(eps)) * w + b
 
 
+# ---------------------------------------------------------------------------------------------
+# Dropout masks of the product's as-shipped (stochastic) mode.  The reference draws them from torch's Philox
+# stream (fresh nn.Dropout at simple_transformer_with_state.py:73,77; the encoder layers' p = 0.1 dropouts
+# while the module is in train mode, offline_testing_simple.py:98); the product draws them from a counter
+# hash documented in include/tip_b200.h (tip_dropout).  This is the numpy restatement of THAT generator, so a
+# stochastic device forward can be checked mask for mask (the statistics -- keep rate 1-p, scale 1/(1-p), sites
+# -- are checked on these masks in tests/test_oracle.py).
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+SEED_IN, SEED_PAST = 0x1111, 0x2222
+SEED_CHUNK = 0x632BE59BD9B4E019
+
+
+def seed_attn(l): return 101 * (l + 1)
+def seed_out(l): return 211 * (l + 1)
+def seed_ff1(l): return 307 * (l + 1)
+def seed_ff2(l): return 401 * (l + 1)
+
+
+def hash_u64(seed, idx):
+    """splitmix64 finaliser of seed + 0x9E3779B97F4A7C15 * (idx + 1), modulo 2^64 (tip_common.cuh hash_u64)."""
+    with np.errstate(over="ignore"):
+        idx = np.asarray(idx, dtype=np.uint64)
+        z = np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + np.uint64(0x9E3779B97F4A7C15) * (idx + np.uint64(1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def drop_threshold(p):
+    p = np.float32(p)
+    return 0 if p <= 0 else (65536 if p >= 1 else int(np.float32(p * np.float32(65536.0) + np.float32(0.5))))
+
+
+def dropout_factors(seed, idx, p, dtype=np.float32):
+    """nn.Dropout(p) factors (0 or 1/(1-p)) of the elements ``idx`` (any integer array) of the site ``seed``."""
+    idx = np.asarray(idx, dtype=np.uint64)
+    thr = drop_threshold(p)
+    if thr == 0:
+        return np.ones(idx.shape, dtype=dtype)
+    h = hash_u64(seed, idx >> np.uint64(2))
+    u = (h >> (np.uint64(16) * (idx & np.uint64(3)))) & np.uint64(0xFFFF)
+    inv = np.float32(0.0) if p >= 1 else np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    return np.where(u < np.uint64(thr), np.float32(0.0), inv).astype(dtype)
+
+
 def forward(sd, x_imu, x_s, n_heads=16, with_rnn=True, keep_mask=None, past_scale=1.0,
-            dtype=np.float32, return_intermediates=False):
-    """Deterministic restatement of TF_RNN_Past_State.forward.
+            dtype=np.float32, return_intermediates=False, dropout=None):
+    """Restatement of TF_RNN_Past_State.forward: deterministic (``dropout=None``), or as shipped with the
+    product's mask generator: ``dropout = dict(seed=, in_dropout=, past_state_dropout=, encoder_dropout=)``
+    (reference :73, :77 and the nn.TransformerEncoderLayer dropouts: on the attention probabilities, on the
+    attention block's output before the residual (dropout1), after the FFN's ReLU, on the FFN's output
+    before the residual (dropout2)).  B <= 1024 (one chunk of the product).
 
     sd         : dict key -> ndarray in the reference's state-dict layout.
     x_imu, x_s : (B, L, 72|90), (B, L, size_s).  Not modified (reference clones, :63-64).
@@ -130,8 +179,20 @@ def forward(sd, x_imu, x_s, n_heads=16, with_rnn=True, keep_mask=None, past_scal
     x_s[np.isnan(x_s)] = 0                                          # :65
     B, L = x_imu.shape[0], x_imu.shape[1]
     x_s[:, :, 18 * 6: 18 * 6 + 3] *= 0                              # :75 root velocity removed
+    dp = dict(seed=0, in_dropout=0.0, past_state_dropout=0.0, encoder_dropout=0.0)
+    dp.update(dropout or {})
+    seed, p_enc = int(dp["seed"]), float(dp["encoder_dropout"])
+    n_imu, size_s = x_imu.shape[2], x_s.shape[2]
+    kin_pad = -(-(n_imu + size_s) // 64) * 64
+    rows = np.arange(B * L, dtype=np.uint64).reshape(B, L, 1)
+    if dp["in_dropout"] > 0:                                        # :73
+        idx = rows * np.uint64(kin_pad) + np.arange(n_imu, dtype=np.uint64)
+        x_imu = x_imu * dropout_factors(seed + SEED_IN, idx, dp["in_dropout"], dtype)
     if keep_mask is not None:                                       # :77 with an explicit mask
         x_s = x_s * (np.asarray(keep_mask, dtype=dtype) * dtype(past_scale))
+    elif dp["past_state_dropout"] > 0:                              # :77 with the product's generator
+        idx = rows * np.uint64(kin_pad) + np.uint64(n_imu) + np.arange(size_s, dtype=np.uint64)
+        x_s = x_s * dropout_factors(seed + SEED_PAST, idx, dp["past_state_dropout"], dtype)
     x = np.concatenate((x_imu, x_s), axis=2)                        # :78
     x = x @ W["in_linear.weight"].T + W["in_linear.bias"]           # :79   (B, L, E)
     E = x.shape[-1]
@@ -156,11 +217,23 @@ def forward(sd, x_imu, x_s, n_heads=16, with_rnn=True, keep_mask=None, past_scal
         s = s - s.max(axis=-1, keepdims=True)
         pr = np.exp(s)
         pr = pr / pr.sum(axis=-1, keepdims=True)
+        if p_enc > 0:                                               # attention-probability dropout
+            bh = (np.arange(B, dtype=np.uint64)[:, None] * np.uint64(n_heads) + np.arange(n_heads, dtype=np.uint64))
+            idx = ((bh[:, :, None] * np.uint64(40) + np.arange(L, dtype=np.uint64)[None, None, :])[..., None] * np.uint64(40)
+                   + np.arange(L, dtype=np.uint64))
+            pr = pr * dropout_factors(seed + seed_attn(i), idx, p_enc, dtype)
         o = (pr @ v).transpose(0, 2, 1, 3).reshape(B, L, E)
         a = o @ W[p + "self_attn.out_proj.weight"].T + W[p + "self_attn.out_proj.bias"]
+        if p_enc > 0:                                               # dropout1
+            a = a * dropout_factors(seed + seed_out(i), rows * np.uint64(E) + np.arange(E, dtype=np.uint64), p_enc, dtype)
         x = _layer_norm(x + a, W[p + "norm1.weight"], W[p + "norm1.bias"])
         f = np.maximum(x @ W[p + "linear1.weight"].T + W[p + "linear1.bias"], 0)
+        if p_enc > 0:                                               # dropout inside the FFN (after the activation)
+            Fh = f.shape[-1]
+            f = f * dropout_factors(seed + seed_ff1(i), rows * np.uint64(Fh) + np.arange(Fh, dtype=np.uint64), p_enc, dtype)
         f = f @ W[p + "linear2.weight"].T + W[p + "linear2.bias"]
+        if p_enc > 0:                                               # dropout2
+            f = f * dropout_factors(seed + seed_ff2(i), rows * np.uint64(E) + np.arange(E, dtype=np.uint64), p_enc, dtype)
         x = _layer_norm(x + f, W[p + "norm2.weight"], W[p + "norm2.bias"])
         if return_intermediates:
             inter[f"layer{i}"] = x.copy()

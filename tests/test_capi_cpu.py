@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert set(names) == set(capi.SIGNATURES), set(names) ^ set(capi.SIGNATURES)
-    assert lib.tip_abi_version() == 1
+    assert lib.tip_abi_version() == 2
 
 
 def test_create_rejects_unsupported_dims_without_touching_a_device():

@@ -94,6 +94,56 @@ def test_oracle_stream_trace():
         assert np.abs(y[0, -1] - g["y_last"][t]).max() < TOL
 
 
+def test_stochastic_generator_statistics():
+    """The product's dropout-mask generator as the oracle restates it (include/tip_b200.h, tip_dropout):
+    drop rates p = 0.8 (past state, reference :77) and 0.1 (nn.TransformerEncoderLayer default) within 4 sigma,
+    kept elements scaled by 1/(1-p) (x5 resp. x1.11), distinct sites / seeds give independent masks, and the
+    mean over masks is the identity (nn.Dropout is unbiased)."""
+    n = 1 << 20
+    idx = np.arange(n)
+    for p, site in ((0.8, O.SEED_PAST), (0.1, O.seed_out(0)), (0.1, O.seed_ff1(3)), (0.1, O.seed_attn(2))):
+        f = O.dropout_factors(1234567 + site, idx, p)
+        drop = (f == 0).mean()
+        assert abs(drop - p) < 4 * np.sqrt(p * (1 - p) / n) + 2e-5, (p, drop)
+        kept = f[f != 0]
+        assert np.all(kept == np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
+        assert abs(kept[0] - 1 / (1 - p)) < 1e-6 * 5
+    a = O.dropout_factors(99 + O.SEED_PAST, idx, 0.8) == 0
+    b = O.dropout_factors(100 + O.SEED_PAST, idx, 0.8) == 0
+    c = O.dropout_factors(99 + O.seed_out(0), idx, 0.8) == 0
+    for u, v in ((a, b), (a, c)):
+        both = (u & v).mean()
+        assert abs(both - 0.64) < 5e-3                                  # independent masks
+    # consecutive elements (the four 16-bit lanes of one hash) are independent too
+    assert abs((a[0::4] & a[1::4]).mean() - 0.64) < 5e-3 and abs((a[2::4] & a[3::4]).mean() - 0.64) < 5e-3
+    x = np.random.RandomState(0).standard_normal(4096).astype(np.float32)
+    acc = np.zeros(4096)
+    for s in range(400):
+        acc += x * O.dropout_factors(s * 7919 + O.SEED_PAST, np.arange(4096), 0.8)
+    err = np.abs(acc / 400 - x)
+    assert err.max() < 6 * np.abs(x).max() * 2.0 / np.sqrt(400)        # sd of one draw = 2|x| at p = 0.8
+
+
+def test_stochastic_oracle_reduces_to_deterministic_and_is_seeded():
+    sd = O.random_state_dict(5)
+    x_imu, x_s = O.synth_inputs(6, 2, 40)
+    y0 = O.forward(sd, x_imu, x_s)
+    np.testing.assert_array_equal(O.forward(sd, x_imu, x_s, dropout=dict(seed=3)), y0)
+    dp = dict(seed=3, past_state_dropout=0.8, encoder_dropout=0.1)
+    y1, y2 = O.forward(sd, x_imu, x_s, dropout=dp), O.forward(sd, x_imu, x_s, dropout=dp)
+    np.testing.assert_array_equal(y1, y2)
+    y3 = O.forward(sd, x_imu, x_s, dropout=dict(dp, seed=4))
+    assert np.abs(y1 - y0).max() > 1e-2 and np.abs(y1 - y3).max() > 1e-2 and np.isfinite(y1).all()
+    # an explicit keep-mask equal to the generator's past-state mask reproduces the drawn-mask forward (:77)
+    kin_pad = 256
+    rows = np.arange(2 * 40, dtype=np.uint64).reshape(2, 40, 1)
+    idx = rows * np.uint64(kin_pad) + np.uint64(90) + np.arange(131, dtype=np.uint64)
+    keep = (O.dropout_factors(3 + O.SEED_PAST, idx, 0.8) != 0).astype(np.float32)
+    ya = O.forward(sd, x_imu, x_s, keep_mask=keep, past_scale=float(np.float32(1) / (np.float32(1) - np.float32(0.8))))
+    yb = O.forward(sd, x_imu, x_s, dropout=dict(seed=3, past_state_dropout=0.8))
+    assert np.abs(ya - yb).max() < 1e-5
+
+
 def test_window_assembler_shapes_and_warmup():
     rs = np.random.RandomState(0)
     wa = O.WindowAssembler()

@@ -78,7 +78,7 @@ def test_pybullet_shim_forward_kinematics():
     """N2: the kinematic PyBullet stand-in -- link frames compose parent * origin * joint rotation."""
     if not os.path.isdir(REF):
         pytest.skip("reference tree (URDF) not present on this box")
-    sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+    sys.path.insert(0, os.path.join(ROOT, "tools", "ref_env", "shims"))
     try:
         import importlib
         pb = importlib.import_module("pybullet")
@@ -101,7 +101,7 @@ def test_pybullet_shim_forward_kinematics():
         np.testing.assert_allclose(np.array(ls2[1][4]) - hip, Rotation.from_quat(q).apply(off), atol=1e-12)
         np.testing.assert_allclose(np.linalg.norm(np.array(ls2[1][4]) - hip), np.linalg.norm(off), atol=1e-12)
     finally:
-        sys.path.remove(os.path.join(ROOT, "oracle", "shims"))
+        sys.path.remove(os.path.join(ROOT, "tools", "ref_env", "shims"))
         sys.modules.pop("pybullet", None)
 
 

@@ -16,17 +16,19 @@ def Q_op(Q, op, xyzw_in=True):
 
 
 def Q_mult(Q1, Q2):
-    """Hamilton product Q1 * Q2 (xyzw)."""
-    ax, ay, az, aw = Q1
-    bx, by, bz, bw = Q2
-    return np.array([
+    """Hamilton product Q1 * Q2 (xyzw), un-normalised, any leading batch dimensions (data_utils.py:395 passes a
+    quaternion DIFFERENCE, so nothing may be re-normalised here)."""
+    Q1, Q2 = np.asarray(Q1, dtype=float), np.asarray(Q2, dtype=float)
+    ax, ay, az, aw = Q1[..., 0], Q1[..., 1], Q1[..., 2], Q1[..., 3]
+    bx, by, bz, bw = Q2[..., 0], Q2[..., 1], Q2[..., 2], Q2[..., 3]
+    return np.stack([
         aw * bx + ax * bw + ay * bz - az * by,
         aw * by - ax * bz + ay * bw + az * bx,
         aw * bz + ax * by - ay * bx + az * bw,
         aw * bw - ax * bx - ay * by - az * bz,
-    ])
+    ], axis=-1)
 
 
 def Q_diff(Q1, Q2):
-    """Q1^-1 * Q2."""
+    """Q1^-1 * Q2 (batched; data_utils.py:318 loss_angle)."""
     return Q_mult(np.asarray(Q1, dtype=float) * np.array([-1.0, -1.0, -1.0, 1.0]), Q2)

@@ -28,9 +28,10 @@ struct FwdGraphKey {
     const void *x_imu, *x_s, *y, *keep;
     int B, L, engine;
     float past_scale;
+    float p_in, p_past, p_enc;          // dropout rates are baked into the captured launches (the SEED is not: device memory)
     bool operator==(const FwdGraphKey& o) const {
         return x_imu == o.x_imu && x_s == o.x_s && y == o.y && keep == o.keep && B == o.B && L == o.L &&
-               engine == o.engine && past_scale == o.past_scale;
+               engine == o.engine && past_scale == o.past_scale && p_in == o.p_in && p_past == o.p_past && p_enc == o.p_enc;
     }
 };
 struct FwdGraph {
@@ -41,13 +42,37 @@ struct FwdGraph {
 };
 constexpr int FWD_GRAPH_SLOTS = 32;     // captured forwards kept per handle (LRU); a lane rotating 16 input sets needs 16
 
+// Packed weights: owned by the handle tip_create made, shared (read-only) by the lanes tip_create_lane derives from it.
+struct SharedWeights {
+    float* blob = nullptr;
+    int refs = 1;
+    bool packed = false;
+    uint64_t pack_seq = 0;              // bumped by every tip_pack_weights
+    cudaEvent_t ev_pack = nullptr;      // recorded on the packing stream at the end of the pack
+};
+
+struct DropP {                          // dropout rates of a call (all 0 = deterministic)
+    float p_in = 0.f, p_past = 0.f, p_enc = 0.f;
+    uint64_t seed = 0;
+    bool any() const { return p_in > 0.f || p_past > 0.f || p_enc > 0.f; }
+    bool same_p(const DropP& o) const { return p_in == o.p_in && p_past == o.p_past && p_enc == o.p_enc; }
+};
+static DropP drop_of(const tip_dropout* d) {
+    DropP r;
+    if (d) { r.p_in = d->in_dropout; r.p_past = d->past_state_dropout; r.p_enc = d->encoder_dropout; r.seed = d->seed; }
+    return r;
+}
+
 struct tip_model {
+    SharedWeights* sw = nullptr;
+    bool is_lane = false;
+    uint64_t pack_ordered_seq = 0;      // last pack this handle's streams are known to be ordered after (pack complete)
+    uint64_t* d_seed = nullptr;         // base seed of the current stochastic call (device memory; graphs read it)
     tip_dims cdims{};
     Dims d{};
     PackOff off{};
     int device = 0;
-    float* blob = nullptr;
-    bool packed = false;
+    float* blob = nullptr;    // = sw->blob
     int engine = 0;           // 0 auto, 1 FFMA, 2 tcgen05
     int use_graphs = 1;
     int launches = 0;
@@ -84,12 +109,13 @@ struct tip_model {
     bool fb_set = false;
     cudaGraphExec_t st_graph = nullptr;   // captured steady-state step (L == MAXL)
     int st_graph_launches = 0;
+    DropP st_graph_p;                     // dropout rates baked into st_graph
     FwdGraph fwd_graphs[FWD_GRAPH_SLOTS];
     uint64_t fwd_tick = 0;
     // host entry, two-part pipeline: copy / compute streams, events, and one captured forward per batch part
     cudaStream_t s_in = nullptr, s_out = nullptr, s_part[2] = {nullptr, nullptr};
     cudaEvent_t ev_start = nullptr, ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    struct PartGraph { cudaGraphExec_t exec = nullptr; int B = 0, L = 0, w0 = 0, nw = 0, launches = 0, seen = 0; } part_graph[2];
+    struct PartGraph { cudaGraphExec_t exec = nullptr; int B = 0, L = 0, w0 = 0, nw = 0, launches = 0, seen = 0; DropP p; } part_graph[2];
     // host entry, job pipeline (tip_forward_host_submit / _wait): per-slot device staging + completion events; one upload,
     // one forward and one download stream shared by all slots (the forwards share the workspace, so they serialise)
     struct HostSlot {
@@ -211,14 +237,65 @@ extern "C" int tip_create(const tip_dims* dims, tip_model** out) {
     m->d.khead = dims->with_rnn ? R : E;
     m->rnn_stream_fallback = getenv("TIP_RNN_STREAM") ? atoi(getenv("TIP_RNN_STREAM")) : 0;
     compute_offsets(m);
-    cudaError_t e = cudaMalloc(&m->blob, m->off.total * sizeof(float));
+    m->sw = new SharedWeights();
+    cudaError_t e = cudaMalloc(&m->sw->blob, m->off.total * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_seed, sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->sw->ev_pack, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         g_create_error = std::string("cudaMalloc(weights): ") + cudaGetErrorString(e);
+        if (m->sw->blob) cudaFree(m->sw->blob);
+        if (m->d_seed) cudaFree(m->d_seed);
+        delete m->sw;
         delete m;
         return TIP_ERR_OOM;
     }
+    m->blob = m->sw->blob;
     cudaMemset(m->blob, 0, m->off.total * sizeof(float));
+    cudaMemset(m->d_seed, 0, sizeof(uint64_t));
     *out = m;
+    return TIP_OK;
+}
+
+// A lane: a second handle on the same device that SHARES the owner's packed weights (read-only; no second copy, no
+// second pack) but has its own workspace, tensor maps, captured graphs, job slots and seed -- forwards of different
+// lanes may overlap on different streams.  The weights stay alive until the last handle sharing them is destroyed.
+extern "C" int tip_create_lane(tip_model* owner, tip_model** out) {
+    if (!owner || !out) { g_create_error = "null argument"; return TIP_ERR_INVALID_ARG; }
+    *out = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != owner->device) { g_create_error = "tip_create_lane: the owner lives on another device"; return TIP_ERR_INVALID_ARG; }
+    tip_model* m = new tip_model();
+    m->cdims = owner->cdims;
+    m->d = owner->d;
+    m->off = owner->off;
+    m->device = owner->device;
+    m->engine = owner->engine;
+    m->rnn_stream_fallback = owner->rnn_stream_fallback;
+    m->is_lane = true;
+    if (cudaMalloc(&m->d_seed, sizeof(uint64_t)) != cudaSuccess) {
+        g_create_error = "cudaMalloc(seed) failed";
+        delete m;
+        return TIP_ERR_OOM;
+    }
+    cudaMemset(m->d_seed, 0, sizeof(uint64_t));
+    m->sw = owner->sw;
+    m->sw->refs++;
+    m->blob = m->sw->blob;
+    *out = m;
+    return TIP_OK;
+}
+
+// Make `s` wait for the last weight pack (it may have run on another stream: another lane's, or the caller's stream at
+// load_state_dict time).  Once the pack is known to be complete the check is one integer compare.
+static int order_after_pack(tip_model* m, cudaStream_t s) {
+    SharedWeights* w = m->sw;
+    if (m->pack_ordered_seq == w->pack_seq) return TIP_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return TIP_OK;   // (never with a pending pack)
+    const uint64_t seq = w->pack_seq;
+    TIP_CUDA_TRY(m, cudaStreamWaitEvent(s, w->ev_pack, 0));
+    if (cudaEventQuery(w->ev_pack) == cudaSuccess) m->pack_ordered_seq = seq; else cudaGetLastError();
     return TIP_OK;
 }
 
@@ -241,6 +318,9 @@ static void free_stream_state(tip_model* m) {
 
 extern "C" void tip_destroy(tip_model* m) {
     if (!m) return;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);              // garbage collection must not change the caller's current device
+    const int m_device_of_destroyed = m->device;
     cudaSetDevice(m->device);
     free_stream_state(m);
     for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
@@ -255,11 +335,18 @@ extern "C" void tip_destroy(tip_model* m) {
         for (float* p : {hsl.d_ximu, hsl.d_xs, hsl.d_y}) if (p) cudaFree(p);
         for (cudaEvent_t e : {hsl.ev_in, hsl.ev_fwd, hsl.ev_out}) if (e) cudaEventDestroy(e);
     }
-    if (m->blob) cudaFree(m->blob);
+    if (m->sw && --m->sw->refs == 0) {
+        cudaDeviceSynchronize();           // (another lane's forward may have been the last reader)
+        if (m->sw->blob) cudaFree(m->sw->blob);
+        if (m->sw->ev_pack) cudaEventDestroy(m->sw->ev_pack);
+        delete m->sw;
+    }
+    if (m->d_seed) cudaFree(m->d_seed);
     if (m->ws) cudaFree(m->ws);
     for (float* p : {m->d_ximu, m->d_xs, m->d_y}) if (p) cudaFree(p);
     for (float* p : {m->h_in, m->h_out}) if (p) cudaFreeHost(p);
     delete m;
+    if (prev_dev >= 0 && prev_dev != m_device_of_destroyed) cudaSetDevice(prev_dev);
 }
 
 extern "C" int tip_num_weight_tensors(const tip_model* m) {
@@ -272,6 +359,7 @@ extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64
     cudaStream_t st = (cudaStream_t)stream_;
     const Dims& d = m->d;
     if (n != tip_num_weight_tensors(m)) { m->set_error("wrong number of weight tensors"); return TIP_ERR_INVALID_ARG; }
+    if (m->is_lane) { m->set_error("tip_pack_weights: a lane shares its owner's weights; pack the owner"); return TIP_ERR_INVALID_ARG; }
     { const int qrc = quiesce_host_jobs(m); if (qrc != TIP_OK) return qrc; }
     // expected element counts in state-dict order
     std::vector<int64_t> exp;
@@ -289,6 +377,9 @@ extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64
             return TIP_ERR_INVALID_ARG;
         }
     TIP_CUDA_TRY(m, cudaSetDevice(m->device));
+    // forwards still in flight on OTHER streams (lanes sharing these weights, the job pipeline, the two-part host entry)
+    // read the blob this call overwrites; a caller that only ever uses one stream keeps the pack fully asynchronous
+    if (m->sw->refs > 1 || m->hs_fwd || m->s_in) TIP_CUDA_TRY(m, cudaDeviceSynchronize());
     float* B = m->blob;
     const PackOff& o = m->off;
     auto copy = [&](size_t dst, const float* src, size_t cnt) {
@@ -298,7 +389,7 @@ extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64
     auto split = [&](size_t src, size_t hi, size_t lo, size_t cnt, int sc_idx, float act_scale) {
         float* inv = B + o.scales + sc_idx;
         float* wsc = B + o.scales + SC_COUNT + sc_idx;
-        pack_scale_kernel<<<1, 256, 0, st>>>(B + src, (int64_t)cnt, act_scale, inv, wsc);
+        pack_scale_kernel<<<1, 1024, 0, st>>>(B + src, (int64_t)cnt, act_scale, inv, wsc);
         pack_split_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(B + src, reinterpret_cast<__half*>(B + hi),
                                                                         reinterpret_cast<__half*>(B + lo), (int64_t)cnt, wsc);
     };
@@ -342,23 +433,12 @@ extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64
     pack_pad_rows_kernel<<<1, 256, 0, st>>>(t[i + 1], B + o.bl, d.size_s, HEAD_NPAD, 1);
     split(o.wl, o.wl_hi, o.wl_lo, (size_t)HEAD_NPAD * d.khead, SC_HEAD, ACT_SCALE);
     TIP_CUDA_TRY(m, cudaGetLastError());
-    m->packed = true;
-    m->maps_ready = false;
-    drop_graphs(m);
-    return TIP_OK;
-}
-
-extern "C" int tip_packed_blob(tip_model* m, void** blob, size_t* bytes) {
-    if (!m || !blob || !bytes) return TIP_ERR_INVALID_ARG;
-    *blob = m->blob;
-    *bytes = m->off.total * sizeof(float);
-    return TIP_OK;
-}
-extern "C" int tip_mark_packed(tip_model* m) {
-    if (!m) return TIP_ERR_INVALID_ARG;
-    m->packed = true;
-    m->maps_ready = false;
-    return TIP_OK;
+    // every stream that reads the weights later (lanes, the job pipeline's forward stream, another caller stream)
+    // waits for this event first (order_after_pack)
+    TIP_CUDA_TRY(m, cudaEventRecord(m->sw->ev_pack, st));
+    m->sw->pack_seq++;
+    m->sw->packed = true;
+    return TIP_OK;        // (addresses unchanged: tensor maps and captured graphs of every handle stay valid)
 }
 extern "C" int tip_set_gemm_engine(tip_model* m, int engine) {
     if (!m || engine < 0 || engine > 2) return TIP_ERR_INVALID_ARG;
@@ -481,6 +561,8 @@ static void launch_sgemm(tip_model* m, cudaStream_t st, const float* A, int lda,
 
 static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, float* out, float* out_lo,
                              int B, int L, float drop_p, uint64_t seed, int row0 = 0) {
+    const uint64_t* sp = m->d_seed;            // base seed (device); `seed` = site offset
+    const int b0 = row0 / L;                   // first window of this launch (dropout indices are batch-global)
     pdl_kind() = 2;
     if (out_lo) {
         // tcgen05 engine: qkv and the output are FP16 hi/lo planes; warp-level tensor-core kernel
@@ -496,16 +578,16 @@ static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, fl
         __half* oh = reinterpret_cast<__half*>(out) + (size_t)row0 * E;
         __half* ol = reinterpret_cast<__half*>(out_lo) + (size_t)row0 * E;
         // smaller CTAs (fewer heads each) quantise better over the SMs; the qkv pieces stay >= 64 bytes
-        if (hpb == 8)      launch_k(attention_mma_kernel<8>, dim3(dim3(B, NH / 8)), dim3(256), AttnCfg<8>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, seed);
-        else if (hpb == 2) launch_k(attention_mma_kernel<2>, dim3(dim3(B, NH / 2)), dim3(64), AttnCfg<2>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, seed);
-        else               launch_k(attention_mma_kernel<4>, dim3(dim3(B, NH / 4)), dim3(128), AttnCfg<4>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, seed);
+        if (hpb == 8)      launch_k(attention_mma_kernel<8>, dim3(dim3(B, NH / 8)), dim3(256), AttnCfg<8>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, sp, seed, b0);
+        else if (hpb == 2) launch_k(attention_mma_kernel<2>, dim3(dim3(B, NH / 2)), dim3(64), AttnCfg<2>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, sp, seed, b0);
+        else               launch_k(attention_mma_kernel<4>, dim3(dim3(B, NH / 4)), dim3(128), AttnCfg<4>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, sp, seed, b0);
         m->launches++;
         return;
     }
     static const int akind = getenv("TIP_ATTN") ? atoi(getenv("TIP_ATTN")) : 0;
-    if (B >= 32 && akind == 1) attention_kernel<4, 4><<<dim3(B, NH / 4), 320, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
-    else if (B >= 32) attention_kernel<2, 4><<<dim3(B, NH / 4), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
-    else         attention_kernel<4, 2><<<dim3(B, NH / 2), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, seed);
+    if (B >= 32 && akind == 1) attention_kernel<4, 4><<<dim3(B, NH / 4), 320, 0, st>>>(qkv, out, out_lo, L, drop_p, sp, seed, b0);
+    else if (B >= 32) attention_kernel<2, 4><<<dim3(B, NH / 4), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, sp, seed, b0);
+    else         attention_kernel<4, 2><<<dim3(B, NH / 2), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, sp, seed, b0);
     m->launches++;
 }
 
@@ -622,8 +704,8 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
 
 // One pass over <= CHUNK_WINDOWS windows.
 static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, float* y, int B, int L,
-                         const float* keep_mask, float past_scale, const tip_dropout* drop,
-                         cudaStream_t st, int w0 = 0, int nw = -1) {
+                         const float* keep_mask, float past_scale, const DropP& drop,
+                         cudaStream_t st, int w0 = 0, int nw = -1, uint64_t seed_chunk = 0) {
     // [w0, w0 + nw): the windows of the batch this call processes (default: all).  x_imu / x_s / y / keep_mask point at
     // window 0; the part uses workspace rows [R0, M).  A part that does not start at window 0 must start on a 128-row
     // tile boundary (tcgen05 engine only); parts of one batch may run concurrently on different streams.
@@ -638,10 +720,8 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
     pdl_rows() = M - R0;                      // programmatic dependent launch only pays for small forwards
     int rc = ensure_workspace(m, B * L);
     if (rc != TIP_OK) return rc;
-    const float p_in = drop ? drop->in_dropout : 0.f;
-    const float p_past = drop ? drop->past_state_dropout : 0.f;
-    const float p_enc = drop ? drop->encoder_dropout : 0.f;
-    const uint64_t seed = drop ? drop->seed : 0;
+    const float p_in = drop.p_in, p_past = drop.p_past, p_enc = drop.p_enc;
+    const uint64_t seed = seed_chunk;          // site offsets are added to this; the call's base seed is read from m->d_seed on the device
     const bool umma = (m->engine == 2) || (m->engine == 0 && UMMA_AVAILABLE);
     if (umma) {
         if (!m->maps_ready) {
@@ -670,10 +750,13 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
         pdl_kind() = 8;
         launch_k(condition_kernel, dim3(blocks), dim3(256), 0, st, x_imu + (size_t)R0 * d.n_imu, x_s + (size_t)R0 * d.size_s,
                  keep_mask ? keep_mask + (size_t)R0 * d.size_s : nullptr, past_scale, xo, xl, nr,
-                 d.n_imu, d.size_s, d.kin_pad, p_in, p_past, seed);
+                 d.n_imu, d.size_s, d.kin_pad, p_in, p_past, (const uint64_t*)m->d_seed, seed, R0);
         m->launches++;
     }
     auto gemm = [&](int which, int layer, const float* A, int K, const float* Wp, int N, Epi ep, bool ln) {
+        ep.seed_ptr = m->d_seed;
+        ep.drop_thr = drop_threshold(ep.drop_p);
+        ep.drop_inv = drop_inv_keep(ep.drop_p);
         if (umma) {
             const int sc = which == UG_IN ? SC_IN : which == UG_IH ? SC_IH : (which == UG_HEAD_R || which == UG_HEAD_E) ? SC_HEAD
                            : SC_LAYER0 + 4 * layer + (which == UG_QKV ? 0 : which == UG_OUT ? 1 : which == UG_FF1 ? 2 : 3);
@@ -730,20 +813,20 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
         if (umma) ep.out_lo = m->qkv + (size_t)m->cap_rows * 3 * E / 2;     // FP16 planes for the mma attention
         gemm(UG_QKV, l, m->xa, E, W + Lo.wqkv, 3 * E, ep, false);
         mark(m, st, "attention", l);
-        launch_attention(m, st, m->qkv, m->att, lo_att, nw, L, p_enc, seed + 101 * (l + 1), R0);
+        launch_attention(m, st, m->qkv, m->att, lo_att, nw, L, p_enc, seed + seed_attn(l), R0);
         mark(m, st, "out_proj_ln", l);
         ep = Epi{}; ep.bias = W + Lo.bo; ep.resid = m->xa; ep.resid_lo = lo_xa; ep.ldr = E;
         ep.gamma = W + Lo.g1; ep.beta = W + Lo.be1; ep.out = m->xb; ep.out_lo = lo_xb; ep.ldc = E;
-        ep.drop_p = p_enc; ep.seed = seed + 211 * (l + 1);
+        ep.drop_p = p_enc; ep.seed = seed + seed_out(l);
         gemm(UG_OUT, l, m->att, E, W + Lo.wo, E, ep, true);
         mark(m, st, "ff1", l);
         ep = Epi{}; ep.bias = W + Lo.b1; ep.relu = 1; ep.out = m->hid; ep.out_lo = lo_hid; ep.ldc = F;
-        ep.drop_p = p_enc; ep.seed = seed + 307 * (l + 1);
+        ep.drop_p = p_enc; ep.seed = seed + seed_ff1(l);
         gemm(UG_FF1, l, m->xb, E, W + Lo.w1, F, ep, false);
         mark(m, st, "ff2_ln", l);
         ep = Epi{}; ep.bias = W + Lo.b2; ep.resid = m->xb; ep.resid_lo = lo_xb; ep.ldr = E;
         ep.gamma = W + Lo.g2; ep.beta = W + Lo.be2; ep.out = m->xa; ep.out_lo = lo_xa; ep.ldc = E;
-        ep.drop_p = p_enc; ep.seed = seed + 401 * (l + 1);
+        ep.drop_p = p_enc; ep.seed = seed + seed_ff2(l);
         gemm(UG_FF2, l, m->hid, F, W + Lo.w2, E, ep, true);
     }
     if (d.with_rnn) {                                                           // reference :95-99
@@ -780,9 +863,11 @@ static int forward_impl(tip_model* m, const float* x_imu, const float* x_s, floa
 extern "C" int tip_forward(tip_model* m, const float* x_imu, const float* x_s, float* y, int B, int L,
                            const float* keep_mask, float past_scale, const tip_dropout* drop, void* stream_) {
     if (!m) return TIP_ERR_INVALID_ARG;
+    int rc = order_after_pack(m, (cudaStream_t)stream_);
+    if (rc != TIP_OK) return rc;
     if (!m->hs_fwd) return forward_impl(m, x_imu, x_s, y, B, L, keep_mask, past_scale, drop, stream_);
     // the job pipeline has been used on this handle: order this forward against it
-    int rc = quiesce_host_jobs(m);
+    rc = quiesce_host_jobs(m);
     if (rc != TIP_OK) return rc;
     rc = forward_impl(m, x_imu, x_s, y, B, L, keep_mask, past_scale, drop, stream_);
     if (rc != TIP_OK) return rc;
@@ -798,7 +883,7 @@ extern "C" int tip_forward(tip_model* m, const float* x_imu, const float* x_s, f
 static int forward_impl(tip_model* m, const float* x_imu, const float* x_s, float* y, int B, int L,
                         const float* keep_mask, float past_scale, const tip_dropout* drop, void* stream_) {
     if (!m) return TIP_ERR_INVALID_ARG;
-    if (!m->packed) { m->set_error("tip_forward before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
+    if (!m->sw->packed) { m->set_error("tip_forward before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
     if (!x_imu || !x_s || !y || B < 1 || L < 1 || L > MAXL) {
         m->set_error("tip_forward: need non-null tensors, B >= 1 and 1 <= L <= 40");
         return TIP_ERR_INVALID_ARG;
@@ -807,12 +892,19 @@ static int forward_impl(tip_model* m, const float* x_imu, const float* x_s, floa
     TIP_CUDA_TRY(m, cudaSetDevice(m->device));
     m->launches = 0;
     const Dims& d = m->d;
-    const bool stochastic = drop && (drop->in_dropout > 0.f || drop->past_state_dropout > 0.f || drop->encoder_dropout > 0.f);
+    DropP dp = drop_of(drop);
+    if (keep_mask) dp.p_past = 0.f;             // an explicit mask replaces the drawn one (:77)
+    cudaStreamCaptureStatus cs0 = cudaStreamCaptureStatusNone;
+    const bool capturing = !(cudaStreamIsCapturing(st, &cs0) == cudaSuccess && cs0 == cudaStreamCaptureStatusNone);
+    if (dp.any() && !capturing) {
+        // this call's base seed -> device memory; captured forwards read it there, so a replay draws fresh masks
+        // (a caller capturing tip_forward into its own graph sets the seed itself: the stream-step graph does)
+        seed_set_kernel<<<1, 1, 0, st>>>(m->d_seed, dp.seed);
+    }
     FwdGraph* slot = nullptr;
-    if (m->use_graphs && !m->profile && !stochastic && B <= CHUNK_WINDOWS && !getenv("TIP_NO_FWD_GRAPH")) {
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
-            const FwdGraphKey key{x_imu, x_s, y, keep_mask, B, L, m->engine, past_scale};
+    const FwdGraphKey key{x_imu, x_s, y, keep_mask, B, L, m->engine, past_scale, dp.p_in, dp.p_past, dp.p_enc};
+    if (m->use_graphs && !m->profile && B <= CHUNK_WINDOWS && !getenv("TIP_NO_FWD_GRAPH")) {
+        if (!capturing) {
             FwdGraph* lru = &m->fwd_graphs[0];
             for (FwdGraph& g : m->fwd_graphs) {
                 if (g.last_use && g.key == key) { slot = &g; break; }
@@ -839,7 +931,7 @@ static int forward_impl(tip_model* m, const float* x_imu, const float* x_s, floa
         TIP_CUDA_TRY(m, cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking));
         cudaGraph_t g = nullptr;
         TIP_CUDA_TRY(m, cudaStreamBeginCapture(cstream, cudaStreamCaptureModeThreadLocal));
-        int rc = forward_chunk(m, x_imu, x_s, y, B, L, keep_mask, past_scale, drop, cstream);
+        int rc = forward_chunk(m, x_imu, x_s, y, B, L, keep_mask, past_scale, dp, cstream);
         cudaError_t ce = cudaStreamEndCapture(cstream, &g);
         cudaGraphExec_t exec = nullptr;
         if (rc == TIP_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, g, 0);
@@ -848,7 +940,7 @@ static int forward_impl(tip_model* m, const float* x_imu, const float* x_s, floa
         if (rc != TIP_OK) return rc;
         if (ce != cudaSuccess) { m->set_error(std::string("forward graph capture: ") + cudaGetErrorString(ce)); return TIP_ERR_CUDA; }
         // forward_chunk may have re-allocated the workspace (drop_graphs) -- then `slot` was reset; re-take it
-        slot->key = FwdGraphKey{x_imu, x_s, y, keep_mask, B, L, m->engine, past_scale};
+        slot->key = key;
         slot->exec = exec;
         slot->launches = m->launches;
         slot->last_use = ++m->fwd_tick;
@@ -859,7 +951,8 @@ static int forward_impl(tip_model* m, const float* x_imu, const float* x_s, floa
         const int nb = std::min(CHUNK_WINDOWS, B - b0);
         const size_t r0 = (size_t)b0 * L;
         int rc = forward_chunk(m, x_imu + r0 * d.n_imu, x_s + r0 * d.size_s, y + r0 * d.size_s, nb, L,
-                               keep_mask ? keep_mask + r0 * d.size_s : nullptr, past_scale, drop, st);
+                               keep_mask ? keep_mask + r0 * d.size_s : nullptr, past_scale, dp, st, 0, -1,
+                               SEED_CHUNK * (uint64_t)(b0 / CHUNK_WINDOWS));
         if (rc != TIP_OK) return rc;
     }
     return TIP_OK;
@@ -876,9 +969,9 @@ static int split_window(int B, int L) {
 
 // forward of the windows [w0, w0 + nw) of the batch staged in d_ximu / d_xs -> d_y, on `st`; replayed from a CUDA graph
 // once the same part has been seen twice
-static int run_part(tip_model* m, int p, int B, int L, int w0, int nw, cudaStream_t st) {
+static int run_part(tip_model* m, int p, int B, int L, int w0, int nw, const DropP& dp, cudaStream_t st) {
     tip_model::PartGraph& pg = m->part_graph[p];
-    const bool same = pg.B == B && pg.L == L && pg.w0 == w0 && pg.nw == nw;
+    const bool same = pg.B == B && pg.L == L && pg.w0 == w0 && pg.nw == nw && pg.p.same_p(dp);
     const bool graphs = m->use_graphs && !m->profile && !getenv("TIP_NO_FWD_GRAPH");
     if (graphs && same && pg.exec) {
         TIP_CUDA_TRY(m, cudaGraphLaunch(pg.exec, st));
@@ -891,7 +984,7 @@ static int run_part(tip_model* m, int p, int B, int L, int w0, int nw, cudaStrea
         cudaGraph_t g = nullptr;
         const int before = m->launches;
         TIP_CUDA_TRY(m, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        int rc = forward_chunk(m, m->d_ximu, m->d_xs, m->d_y, B, L, nullptr, 1.f, nullptr, cs, w0, nw);
+        int rc = forward_chunk(m, m->d_ximu, m->d_xs, m->d_y, B, L, nullptr, 1.f, dp, cs, w0, nw);
         cudaError_t ce = cudaStreamEndCapture(cs, &g);
         cudaGraphExec_t exec = nullptr;
         if (rc == TIP_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, g, 0);
@@ -900,13 +993,13 @@ static int run_part(tip_model* m, int p, int B, int L, int w0, int nw, cudaStrea
         if (rc != TIP_OK) return rc;
         if (ce != cudaSuccess) { m->set_error(std::string("part graph capture: ") + cudaGetErrorString(ce)); return TIP_ERR_CUDA; }
         tip_model::PartGraph& pg2 = m->part_graph[p];          // (drop_graphs may have run inside forward_chunk)
-        pg2.exec = exec; pg2.B = B; pg2.L = L; pg2.w0 = w0; pg2.nw = nw; pg2.launches = m->launches - before; pg2.seen = 2;
+        pg2.exec = exec; pg2.B = B; pg2.L = L; pg2.w0 = w0; pg2.nw = nw; pg2.launches = m->launches - before; pg2.seen = 2; pg2.p = dp;
         TIP_CUDA_TRY(m, cudaGraphLaunch(exec, st));
         return TIP_OK;
     }
-    if (!same) { if (pg.exec) cudaGraphExecDestroy(pg.exec); pg = tip_model::PartGraph{}; pg.B = B; pg.L = L; pg.w0 = w0; pg.nw = nw; }
+    if (!same) { if (pg.exec) cudaGraphExecDestroy(pg.exec); pg = tip_model::PartGraph{}; pg.B = B; pg.L = L; pg.w0 = w0; pg.nw = nw; pg.p = dp; }
     pg.seen = 1;
-    return forward_chunk(m, m->d_ximu, m->d_xs, m->d_y, B, L, nullptr, 1.f, nullptr, st, w0, nw);
+    return forward_chunk(m, m->d_ximu, m->d_xs, m->d_y, B, L, nullptr, 1.f, dp, st, w0, nw);
 }
 
 static bool is_pinned_host(const void* p) {
@@ -922,13 +1015,15 @@ extern "C" int tip_forward_host(tip_model* m, const float* x_imu_h, const float*
         m->set_error("tip_forward_host: bad arguments");
         return TIP_ERR_INVALID_ARG;
     }
-    if (!m->packed) { m->set_error("tip_forward_host before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
+    if (!m->sw->packed) { m->set_error("tip_forward_host before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
     cudaStream_t st = (cudaStream_t)stream_;
     TIP_CUDA_TRY(m, cudaSetDevice(m->device));
     { const int qrc = quiesce_host_jobs(m); if (qrc != TIP_OK) return qrc; }
+    { const int prc = order_after_pack(m, st); if (prc != TIP_OK) return prc; }
     const Dims& d = m->d;
     const size_t rows = (size_t)B * L;
     if (rows > m->host_cap) {
+        drop_graphs(m);                    // captured forwards / parts have the old staging addresses baked in
         for (float* p : {m->d_ximu, m->d_xs, m->d_y}) if (p) cudaFree(p);
         for (float* p : {m->h_in, m->h_out}) if (p) cudaFreeHost(p);
         m->host_cap = 0;
@@ -957,9 +1052,9 @@ extern "C" int tip_forward_host(tip_model* m, const float* x_imu_h, const float*
     // forwards are less efficient than one whole-batch forward (the recurrence costs its 90 us per part, the
     // LayerNorm GEMMs fill 40 SMs), which eats most of the 265 us of copies that now overlap.
     static const int host_parts = getenv("TIP_HOST_PARTS") ? atoi(getenv("TIP_HOST_PARTS")) : 2;
-    const bool stochastic = drop && (drop->in_dropout > 0.f || drop->past_state_dropout > 0.f || drop->encoder_dropout > 0.f);
+    const DropP dp = drop_of(drop);
     const bool umma_engine = (m->engine == 2) || (m->engine == 0 && UMMA_AVAILABLE);
-    const int wsplit = (host_parts == 2 && !last_row_only && !stochastic && umma_engine && B >= 64 && B <= CHUNK_WINDOWS)
+    const int wsplit = (host_parts == 2 && !last_row_only && umma_engine && B >= 64 && B <= CHUNK_WINDOWS)
                            ? split_window(B, L) : 0;
     if (wsplit > 0) {
         if (!m->s_in) {
@@ -975,6 +1070,7 @@ extern "C" int tip_forward_host(tip_model* m, const float* x_imu_h, const float*
         int rc = ensure_workspace(m, (int)rows);
         if (rc != TIP_OK) return rc;
         const int pw0[2] = {0, wsplit}, pnw[2] = {wsplit, B - wsplit};
+        if (dp.any()) seed_set_kernel<<<1, 1, 0, st>>>(m->d_seed, dp.seed);     // both parts draw from this call's seed
         TIP_CUDA_TRY(m, cudaEventRecord(m->ev_start, st));      // earlier work on `st` may still use the staging buffers
         TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->s_in, m->ev_start, 0));
         TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->s_out, m->ev_start, 0));
@@ -989,7 +1085,7 @@ extern "C" int tip_forward_host(tip_model* m, const float* x_imu_h, const float*
         for (int p2 = 0; p2 < 2; ++p2) {
             const size_t r0 = (size_t)pw0[p2] * L, nr = (size_t)pnw[p2] * L;
             TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->s_part[p2], m->ev_in[p2], 0));
-            rc = run_part(m, p2, B, L, pw0[p2], pnw[p2], m->s_part[p2]);
+            rc = run_part(m, p2, B, L, pw0[p2], pnw[p2], dp, m->s_part[p2]);
             if (rc != TIP_OK) return rc;
             TIP_CUDA_TRY(m, cudaEventRecord(m->ev_out[p2], m->s_part[p2]));
             TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->s_out, m->ev_out[p2], 0));
@@ -1043,7 +1139,7 @@ extern "C" int tip_forward_host_submit(tip_model* m, int slot, const float* x_im
         m->set_error("tip_forward_host_submit: need 0 <= slot < TIP_HOST_SLOTS, non-null buffers, B >= 1 and 1 <= L <= 40");
         return TIP_ERR_INVALID_ARG;
     }
-    if (!m->packed) { m->set_error("tip_forward_host_submit before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
+    if (!m->sw->packed) { m->set_error("tip_forward_host_submit before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
     TIP_CUDA_TRY(m, cudaSetDevice(m->device));
     if (!(is_pinned_host(x_imu_h) && is_pinned_host(x_s_h) && is_pinned_host(y_h))) {
         // a pageable buffer would turn every cudaMemcpyAsync into a staged, host-blocking copy: no overlap, and the
@@ -1083,6 +1179,8 @@ extern "C" int tip_forward_host_submit(tip_model* m, int slot, const float* x_im
     TIP_CUDA_TRY(m, cudaEventRecord(s.ev_in, m->hs_in));
     TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->hs_fwd, s.ev_in, 0));
     if (m->ev_user_set) { TIP_CUDA_TRY(m, cudaStreamWaitEvent(m->hs_fwd, m->ev_user, 0)); m->ev_user_set = false; }
+    rc = order_after_pack(m, m->hs_fwd);               // a (re-)pack queued on a caller stream since the last job
+    if (rc != TIP_OK) return rc;
     // graph replay from the slot's third job on (the captured forwards are keyed on the staging addresses)
     rc = forward_impl(m, s.d_ximu, s.d_xs, s.d_y, B, L, nullptr, 1.f, drop, m->hs_fwd);
     if (rc != TIP_OK) return rc;
@@ -1170,11 +1268,14 @@ static int stream_step_core(tip_model* m, float* y_last, int rows_on_host, const
     const size_t S = m->n_streams;
     const size_t n_s = S * d.size_s;
     const int len_before = m->stream_len;
-    const bool stochastic = drop && (drop->in_dropout > 0.f || drop->past_state_dropout > 0.f || drop->encoder_dropout > 0.f);
+    const DropP dp = drop_of(drop);
     const bool steady = (len_before == MAXL);
-    int rc = TIP_OK;
-    if (steady && m->use_graphs && !stochastic) {
-        // steady state: the whole frame (2 window shifts + forward + last-row gather) is one graph launch
+    int rc = order_after_pack(m, st);
+    if (rc != TIP_OK) return rc;
+    if (steady && m->use_graphs) {
+        // steady state: the whole frame (2 window shifts + forward + last-row gather) is one graph launch; dropout rates
+        // are baked in, the seed is read from device memory (set right before the launch)
+        if (m->st_graph && !m->st_graph_p.same_p(dp)) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
         if (!m->st_graph) {
             rc = ensure_workspace(m, (int)S * MAXL);
             if (rc != TIP_OK) return rc;
@@ -1189,17 +1290,19 @@ static int stream_step_core(tip_model* m, float* y_last, int rows_on_host, const
             TIP_CUDA_TRY(m, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
             cudaGraph_t g = nullptr;
             TIP_CUDA_TRY(m, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-            rc = stream_step_device(m, nullptr, cs, MAXL);
+            rc = stream_step_device(m, drop, cs, MAXL);
             cudaError_t ce = cudaStreamEndCapture(cs, &g);
             if (rc == TIP_OK && ce == cudaSuccess) {
                 ce = cudaGraphInstantiate(&m->st_graph, g, 0);
                 m->st_graph_launches = m->launches;
+                m->st_graph_p = dp;
             }
             if (g) cudaGraphDestroy(g);
             cudaStreamDestroy(cs);
             if (rc != TIP_OK) return rc;
             if (ce != cudaSuccess) { m->set_error(std::string("graph capture: ") + cudaGetErrorString(ce)); return TIP_ERR_CUDA; }
         }
+        if (dp.any()) seed_set_kernel<<<1, 1, 0, st>>>(m->d_seed, dp.seed);
         TIP_CUDA_TRY(m, cudaGraphLaunch(m->st_graph, st));
         m->launches = m->st_graph_launches;
     } else {
@@ -1221,7 +1324,7 @@ static int stream_step_core(tip_model* m, float* y_last, int rows_on_host, const
 extern "C" int tip_stream_step(tip_model* m, const float* imu_row, const float* s_row, float* y_last,
                                int rows_on_host, const tip_dropout* drop, void* stream_) {
     if (!m || !imu_row || !s_row || !y_last) return TIP_ERR_INVALID_ARG;
-    if (!m->packed) { m->set_error("tip_stream_step before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
+    if (!m->sw->packed) { m->set_error("tip_stream_step before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
     if (m->n_streams < 1) { m->set_error("tip_stream_step before tip_stream_reset"); return TIP_ERR_INVALID_ARG; }
     cudaStream_t st = (cudaStream_t)stream_;
     TIP_CUDA_TRY(m, cudaSetDevice(m->device));
@@ -1244,7 +1347,7 @@ extern "C" int tip_stream_step(tip_model* m, const float* imu_row, const float* 
 extern "C" int tip_stream_step_raw(tip_model* m, const float* raw_imu, const float* s_row, float* y_last,
                                    int rows_on_host, const tip_dropout* drop, void* stream_, int* produced) {
     if (!m || !raw_imu || !s_row || !y_last || !produced) return TIP_ERR_INVALID_ARG;
-    if (!m->packed) { m->set_error("tip_stream_step_raw before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
+    if (!m->sw->packed) { m->set_error("tip_stream_step_raw before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
     if (m->n_streams < 1) { m->set_error("tip_stream_step_raw before tip_stream_reset"); return TIP_ERR_INVALID_ARG; }
     cudaStream_t st = (cudaStream_t)stream_;
     TIP_CUDA_TRY(m, cudaSetDevice(m->device));
@@ -1297,7 +1400,7 @@ extern "C" int tip_stream_set_state(tip_model* m, const float* s_row0, int rows_
 extern "C" int tip_stream_step_closed(tip_model* m, const float* raw_imu, const float* y_override, double* state_out,
                                       int rows_on_host, const tip_dropout* drop, void* stream_, int* produced) {
     if (!m || !raw_imu || !state_out || !produced) return TIP_ERR_INVALID_ARG;
-    if (!m->packed) { m->set_error("tip_stream_step_closed before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
+    if (!m->sw->packed) { m->set_error("tip_stream_step_closed before tip_pack_weights"); return TIP_ERR_NOT_PACKED; }
     if (m->n_streams < 1 || !m->fb_set) {
         m->set_error("tip_stream_step_closed needs tip_stream_reset and tip_stream_set_state first");
         return TIP_ERR_INVALID_ARG;

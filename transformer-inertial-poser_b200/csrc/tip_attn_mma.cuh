@@ -47,7 +47,8 @@ __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint3
 template <int AM_HPB>
 __global__ void __launch_bounds__(AM_HPB * 32, 1024 / (AM_HPB * 32) < 4 ? 1024 / (AM_HPB * 32) : 4)
 attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict__ qkv_lo,
-                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, int L, float drop_p, uint64_t seed) {
+                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, int L, float drop_p,
+                     const uint64_t* __restrict__ seed_ptr, uint64_t seed_off, int b0) {
     constexpr int AM_ROWB = AttnCfg<AM_HPB>::ROWB, AM_QK_BYTES = AttnCfg<AM_HPB>::QK_BYTES, AM_V_BYTES = AttnCfg<AM_HPB>::V_BYTES;
     constexpr int CPR = AM_HPB * 2;                  // 16-byte chunks per row of a plane tile
     extern __shared__ __align__(16) uint8_t am_smem[];
@@ -101,7 +102,9 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
     }
     __syncthreads();                                 // every warp holds its K fragments: the K planes may become sO
 
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const float inv_keep = drop_inv_keep(drop_p);
+    const uint32_t dthr = drop_threshold(drop_p);
+    const uint64_t seed = drop_p > 0.f ? site_seed(seed_ptr, seed_off) : 0ull;
     // ldmatrix.trans row addresses of this lane: lanes 0-7 -> keys +0..7, lanes 8-15 -> keys +8..15
     const uint32_t vaddr_h = (uint32_t)__cvta_generic_to_shared(sVh) + (uint32_t)((lane & 15) * AM_ROWB + hl * 32);
     const uint32_t vaddr_l = (uint32_t)__cvta_generic_to_shared(sVl) + (uint32_t)((lane & 15) * AM_ROWB + hl * 32);
@@ -138,26 +141,29 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
         }
         ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1)); ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
         mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
-        // exp, row sums (fp32, before dropout), optional attention dropout
+        // exp, row sums (fp32, before dropout), optional attention dropout.  Element index of P[b, h, query, key] =
+        // ((b * 16 + h) * 40 + query) * 40 + key: this lane's two keys of a tile (2*t4, 2*t4 + 1) share one hash group
         float la = 0.f, lb = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 6; ++nt) {
             if (!(nt <= 2 * mt + 1 && nt < 5)) continue;         // s[nt] stays 0 there: contributes nothing to P V
+            float fa[2] = {1.f, 1.f}, fb[2] = {1.f, 1.f};
+            if (drop_p > 0.f) {
+                const int key0 = 8 * nt + 2 * t4;
+                const uint64_t ida = (((uint64_t)(b0 + b) * NH + h0 + hl) * MAXL + ra) * MAXL + key0;
+                const uint64_t idb = (((uint64_t)(b0 + b) * NH + h0 + hl) * MAXL + rb) * MAXL + key0;
+                const float4 a4 = dropout_factor4(seed, ida >> 2, dthr, inv_keep), b4 = dropout_factor4(seed, idb >> 2, dthr, inv_keep);
+                if (ida & 2) { fa[0] = a4.z; fa[1] = a4.w; } else { fa[0] = a4.x; fa[1] = a4.y; }
+                if (idb & 2) { fb[0] = b4.z; fb[1] = b4.w; } else { fb[0] = b4.x; fb[1] = b4.y; }
+            }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int key = 8 * nt + 2 * t4 + e;
                 float pa = exp2f((s[nt][e] - ma) * 1.4426950408889634f);        // exp(-inf) = 0 for masked slots
                 float pb = exp2f((s[nt][2 + e] - mb) * 1.4426950408889634f);
                 la += pa;
                 lb += pb;
-                if (drop_p > 0.f) {
-                    const uint64_t ida = (((uint64_t)b * NH + h0 + hl) * MAXL + ra) * MAXL + key;
-                    const uint64_t idb = (((uint64_t)b * NH + h0 + hl) * MAXL + rb) * MAXL + key;
-                    pa *= dropout_factor(drop_p, inv_keep, seed, ida);
-                    pb *= dropout_factor(drop_p, inv_keep, seed, idb);
-                }
-                s[nt][e] = pa;
-                s[nt][2 + e] = pb;
+                s[nt][e] = pa * fa[e];
+                s[nt][2 + e] = pb * fb[e];
             }
         }
         la += __shfl_xor_sync(0xffffffffu, la, 1); la += __shfl_xor_sync(0xffffffffu, la, 2);

@@ -56,28 +56,56 @@ struct Dims {
     int khead;      // R or E
 };
 
-// counter-based RNG for the reference's dropout sites (statistically equivalent, not bit-equal to
-// torch's Philox stream -- see DESIGN.md "stochastic mode").
-__host__ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
+// Counter-based RNG of the reference's dropout sites (statistically equivalent, not bit-equal to torch's Philox
+// stream -- DESIGN.md "as-shipped mode").  One 64-bit splitmix hash yields FOUR 16-bit uniforms: element `idx` of a
+// site uses lane (idx & 3) of hash(site_seed, idx >> 2) and is DROPPED when its uniform is below
+// thr = round(p * 65536); kept elements are scaled by 1/(1-p) like nn.Dropout.  The site seed is
+// base_seed + site constant, the base seed lives in DEVICE memory (tip_model::d_seed, written by a one-thread
+// kernel before every stochastic forward) so a captured CUDA graph draws fresh masks on every replay.
+// oracle/tip_oracle.py restates exactly this generator, so stochastic forwards are parity-tested mask for mask.
+__host__ __device__ __forceinline__ uint64_t hash_u64(uint64_t seed, uint64_t idx) {
     uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (uint32_t)(z >> 32);
+    return z ^ (z >> 31);
 }
-// returns the multiplicative factor of nn.Dropout(p): 0 with prob p, 1/(1-p) otherwise
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+    return p <= 0.f ? 0u : (p >= 1.f ? 65536u : (uint32_t)(p * 65536.f + 0.5f));
+}
+__host__ __device__ __forceinline__ float drop_inv_keep(float p) { return p > 0.f ? (p < 1.f ? 1.f / (1.f - p) : 0.f) : 1.f; }
+// factors of the four elements 4*group .. 4*group + 3
+__device__ __forceinline__ float4 dropout_factor4(uint64_t seed, uint64_t group, uint32_t thr, float inv_keep) {
+    const uint64_t h = hash_u64(seed, group);
+    const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+    return make_float4((lo & 0xFFFFu) < thr ? 0.f : inv_keep, (lo >> 16) < thr ? 0.f : inv_keep,
+                       (hi & 0xFFFFu) < thr ? 0.f : inv_keep, (hi >> 16) < thr ? 0.f : inv_keep);
+}
+// single element (scalar sites): 0 with probability p, 1/(1-p) otherwise
 __device__ __forceinline__ float dropout_factor(float p, float inv_keep, uint64_t seed, uint64_t idx) {
-    const uint32_t r = hash_u32(seed, idx);
-    return ((float)r * 2.3283064365386963e-10f < p) ? 0.f : inv_keep;
+    const uint64_t h = hash_u64(seed, idx >> 2);
+    const uint32_t u = (uint32_t)(h >> (16 * (idx & 3))) & 0xFFFFu;
+    return u < drop_threshold(p) ? 0.f : inv_keep;
 }
+// site seed = *base (device memory; null = 0) + per-site offset
+__device__ __forceinline__ uint64_t site_seed(const uint64_t* base, uint64_t off) { return (base ? *base : 0ull) + off; }
+// per-site offsets (layer l = 0..): also restated in oracle/tip_oracle.py
+constexpr uint64_t SEED_IN = 0x1111ull, SEED_PAST = 0x2222ull;
+__host__ __device__ constexpr uint64_t seed_attn(int l) { return 101ull * (uint64_t)(l + 1); }
+__host__ __device__ constexpr uint64_t seed_out(int l) { return 211ull * (uint64_t)(l + 1); }
+__host__ __device__ constexpr uint64_t seed_ff1(int l) { return 307ull * (uint64_t)(l + 1); }
+__host__ __device__ constexpr uint64_t seed_ff2(int l) { return 401ull * (uint64_t)(l + 1); }
+constexpr uint64_t SEED_CHUNK = 0x632BE59BD9B4E019ull;     // added per 1024-window chunk of a large batch
 
 // Error-compensated FP16 split of an (already scaled) fp32 value: v ~= hi + lo to ~22 bits.
-// The hi conversion saturates (|v| > 65504 clamps) so out-of-range inputs cannot inject inf/NaN.
+// Both conversions saturate: |v| > 65504 clamps to +-65504 (hi) and the residual to +-65504 (lo), so an
+// out-of-range finite input cannot inject inf/NaN (it clamps near +-131008; DESIGN.md "range contract").
 __device__ __forceinline__ void half_split(float v, __half& hi, __half& lo) {
-    unsigned short h;
+    unsigned short h, l;
     asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
     hi = __ushort_as_half(h);
-    lo = __float2half_rn(v - __half2float(hi));
+    const float r = v - __half2float(hi);
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(r));
+    lo = __ushort_as_half(l);
 }
 // four consecutive values -> 8-byte stores into the hi / lo planes
 __device__ __forceinline__ void half_split_store4(__half* hi_p, __half* lo_p, float4 v) {

@@ -14,44 +14,54 @@ namespace tip {
 // one (M, kin_pad) matrix (zero padded) in fp32 or FP16 hi/lo planes.
 __device__ __forceinline__ float condition_value(const float* __restrict__ x_imu, const float* __restrict__ x_s,
                                                  const float* __restrict__ keep_mask, float past_scale, int r, int c,
-                                                 int n_imu, int size_s, int kin_pad, float p_in, float p_past,
-                                                 float inv_in, float inv_past, uint64_t seed) {
+                                                 int n_imu, int size_s, float f_in, float f_past) {
     float v = 0.f;
-    const int64_t i = (int64_t)r * kin_pad + c;
     if (c < n_imu) {
-        v = __ldg(x_imu + (int64_t)r * n_imu + c);
-        if (p_in > 0.f) v *= dropout_factor(p_in, inv_in, seed ^ 0x1111, i);
+        v = __ldg(x_imu + (int64_t)r * n_imu + c) * f_in;                            // :73
     } else if (c < n_imu + size_s) {
         const int cs = c - n_imu;
         v = __ldg(x_s + (int64_t)r * size_s + cs);
         if (v != v) v = 0.f;                               // :65  x_s[isnan] = 0
         if (cs >= 108 && cs < 111) v = 0.f;                // :75  root velocity removed
         if (keep_mask != nullptr) v *= __ldg(keep_mask + (int64_t)r * size_s + cs) * past_scale;
-        else if (p_past > 0.f) v *= dropout_factor(p_past, inv_past, seed ^ 0x2222, i);   // :77
+        else v *= f_past;                                  // :77
     }
     return v;
 }
 // one thread produces 8 consecutive columns of a row (kin_pad is a multiple of 64): 16-byte stores into
-// the FP16 hi/lo planes (scale 1: raw model input) of the tcgen05 engine, or fp32 for the FFMA engine
+// the FP16 hi/lo planes (scale 1: raw model input) of the tcgen05 engine, or fp32 for the FFMA engine.
+// Dropout element index = row * kin_pad + column of the concatenated (padded) input row (row0 = first global row).
 __global__ void condition_kernel(const float* __restrict__ x_imu, const float* __restrict__ x_s,
                                  const float* __restrict__ keep_mask, float past_scale,
                                  float* __restrict__ out, float* __restrict__ out_lo,
                                  int M, int n_imu, int size_s, int kin_pad,
-                                 float p_in, float p_past, uint64_t seed) {
+                                 float p_in, float p_past, const uint64_t* __restrict__ seed_ptr, uint64_t seed_off, int row0) {
     griddep_wait();
     griddep_launch();
     const int groups = kin_pad >> 3;
     const int64_t total = (int64_t)M * groups;
-    const float inv_in = p_in > 0.f ? 1.f / (1.f - p_in) : 1.f;
-    const float inv_past = p_past > 0.f ? (p_past < 1.f ? 1.f / (1.f - p_past) : 0.f) : 1.f;
+    const uint32_t thr_in = drop_threshold(p_in), thr_past = keep_mask ? 0u : drop_threshold(p_past);
+    const float inv_in = drop_inv_keep(p_in), inv_past = drop_inv_keep(p_past);
+    const uint64_t seed = (thr_in | thr_past) ? site_seed(seed_ptr, seed_off) : 0ull;
     for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(gi / groups);
         const int c0 = (int)(gi - (int64_t)r * groups) << 3;
+        float fin[8], fpast[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { fin[j] = 1.f; fpast[j] = 1.f; }
+        const uint64_t g0 = ((uint64_t)(row0 + r) * kin_pad + c0) >> 2;              // two groups of four elements
+        if (thr_in && c0 < n_imu) {
+            const float4 a = dropout_factor4(seed + SEED_IN, g0, thr_in, inv_in), b = dropout_factor4(seed + SEED_IN, g0 + 1, thr_in, inv_in);
+            fin[0] = a.x; fin[1] = a.y; fin[2] = a.z; fin[3] = a.w; fin[4] = b.x; fin[5] = b.y; fin[6] = b.z; fin[7] = b.w;
+        }
+        if (thr_past && c0 + 8 > n_imu && c0 < n_imu + size_s) {
+            const float4 a = dropout_factor4(seed + SEED_PAST, g0, thr_past, inv_past), b = dropout_factor4(seed + SEED_PAST, g0 + 1, thr_past, inv_past);
+            fpast[0] = a.x; fpast[1] = a.y; fpast[2] = a.z; fpast[3] = a.w; fpast[4] = b.x; fpast[5] = b.y; fpast[6] = b.z; fpast[7] = b.w;
+        }
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            v[j] = condition_value(x_imu, x_s, keep_mask, past_scale, r, c0 + j, n_imu, size_s, kin_pad, p_in, p_past,
-                                   inv_in, inv_past, seed);
+            v[j] = condition_value(x_imu, x_s, keep_mask, past_scale, r, c0 + j, n_imu, size_s, fin[j], fpast[j]);
         const int64_t o = (int64_t)r * kin_pad + c0;
         if (out_lo != nullptr) {
             half_split_store4(reinterpret_cast<__half*>(out) + o, reinterpret_cast<__half*>(out_lo) + o,
@@ -64,6 +74,9 @@ __global__ void condition_kernel(const float* __restrict__ x_imu, const float* _
         }
     }
 }
+
+// one thread: the base seed of this call's dropout masks -> device memory (outside any captured graph)
+__global__ void seed_set_kernel(uint64_t* __restrict__ dst, uint64_t seed) { *dst = seed; }
 
 // ------------------------------------------------------------------------------------------------
 // C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  A and W are K-contiguous (nn.Linear layout).
@@ -79,8 +92,11 @@ struct Epi {
     const float* acc_scale; // tcgen05 engine: device scalar multiplying the accumulator (1/(s_a*s_w))
     int ldc;
     int relu;
-    float drop_p;           // dropout on the GEMM output (after ReLU; before the residual add)
-    uint64_t seed;
+    float drop_p;           // dropout on the GEMM output (after ReLU; before the residual add); element index = row * N + col
+    uint32_t drop_thr;      // = drop_threshold(drop_p), drop_inv = drop_inv_keep(drop_p): set by the host (tcgen05 engine reads them from the constant bank)
+    float drop_inv;
+    const uint64_t* seed_ptr;   // base seed of the call (device memory; null = 0)
+    uint64_t seed;              // + site offset (tip_common.cuh seed_out / seed_ff1 / seed_ff2 [+ chunk]); rows are batch-global
     int dbg;                // experiment flags (TIP_DBG env): 1 skip stores, 2 skip bias loads
     unsigned long long* tbuf;   // optional phase timestamps of CTA 0 (TIP_DBG & 4)
     int tma_out;            // tcgen05 engine: the output goes through TMA store boxes
@@ -190,7 +206,8 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
     }
 
     // ---- epilogue ----
-    const float inv_keep = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
+    const float inv_keep = drop_inv_keep(ep.drop_p);
+    const uint64_t dseed = ep.drop_p > 0.f ? site_seed(ep.seed_ptr, ep.seed) : 0ull;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
         const int row = m0 + (i / 4) * (BM / 2) + ty * 4 + (i & 3);
@@ -201,7 +218,7 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
             const int col = n0 + (j / 4) * (BN / 2) + tx * 4 + (j & 3);
             float x = acc[i][j] + ((col < N) ? __ldg(ep.bias + col) : 0.f);
             if (ep.relu) x = fmaxf(x, 0.f);
-            if (ep.drop_p > 0.f) x *= dropout_factor(ep.drop_p, inv_keep, ep.seed, (uint64_t)row * N + col);
+            if (ep.drop_p > 0.f) x *= dropout_factor(ep.drop_p, inv_keep, dseed, (uint64_t)row * N + col);
             v[j] = x;
         }
         if constexpr (LN) {
@@ -261,7 +278,7 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
 template <int KS, int HPB>
 __global__ void __launch_bounds__(HPB * 20 * KS)
 attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ out_lo,
-                 int L, float drop_p, uint64_t seed) {
+                 int L, float drop_p, const uint64_t* __restrict__ seed_ptr, uint64_t seed_off, int b0) {
     constexpr int NT = HPB * 20 * KS;
     __shared__ __align__(16) float Qs[MAXL][HPB][HD];      // reused for the output tile
     __shared__ __align__(16) float Ks[MAXL][HPB][HD];
@@ -337,7 +354,8 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* 
     float oa[HD], ob[HD], la = 0.f, lb = 0.f;
 #pragma unroll
     for (int i = 0; i < HD; ++i) { oa[i] = 0.f; ob[i] = 0.f; }
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const float inv_keep = drop_inv_keep(drop_p);
+    const uint64_t seed = drop_p > 0.f ? site_seed(seed_ptr, seed_off) : 0ull;
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) {
         const int j = jj * KS + ks;
@@ -347,8 +365,8 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* 
             la += pa;
             lb += pb;
             if (drop_p > 0.f) {   // attention-probability dropout (train mode only)
-                const uint64_t ida = (((uint64_t)b * NH + h0 + hl) * MAXL + ra) * MAXL + j;
-                const uint64_t idb = (((uint64_t)b * NH + h0 + hl) * MAXL + rb) * MAXL + j;
+                const uint64_t ida = (((uint64_t)(b0 + b) * NH + h0 + hl) * MAXL + ra) * MAXL + j;
+                const uint64_t idb = (((uint64_t)(b0 + b) * NH + h0 + hl) * MAXL + rb) * MAXL + j;
                 pa *= dropout_factor(drop_p, inv_keep, seed, ida);
                 pb *= dropout_factor(drop_p, inv_keep, seed, idb);
             }
@@ -1190,23 +1208,32 @@ __global__ void pack_pad_rows_kernel(const float* __restrict__ src, float* __res
 }
 // max |w| of a matrix -> power-of-two scale s_w with s_w * max|w| in [16384, 32768); writes
 // scales[idx] = 1 / (s_w * act_scale) for the GEMM epilogue and scales_w[idx] = s_w for the split.
-__global__ void pack_scale_kernel(const float* __restrict__ src, int64_t n, float act_scale,
-                                  float* __restrict__ inv_scale, float* __restrict__ w_scale) {
-    __shared__ float red[256];
+__global__ void __launch_bounds__(1024)
+pack_scale_kernel(const float* __restrict__ src, int64_t n, float act_scale,
+                  float* __restrict__ inv_scale, float* __restrict__ w_scale) {
+    // one block of 1024 threads, 16-byte loads (every packed matrix is 256-byte aligned with n % 4 == 0)
+    __shared__ float red[32];
     float m = 0.f;
-    for (int64_t i = threadIdx.x; i < n; i += 256) m = fmaxf(m, fabsf(src[i]));
-    red[threadIdx.x] = m;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
-        __syncthreads();
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int64_t i = threadIdx.x; i < (n >> 2); i += 1024) {
+        const float4 v = __ldg(s4 + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
     }
-    if (threadIdx.x == 0) {
-        const float mx = red[0];
-        float sw = 1.f;
-        if (mx > 0.f && mx < INFINITY) sw = exp2f(floorf(log2f(32768.f / mx)));
-        *w_scale = sw;
-        *inv_scale = 1.f / (sw * act_scale);
+    for (int64_t i = (n & ~(int64_t)3) + threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(src[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) {
+            float sw = 1.f;
+            if (m > 0.f && m < INFINITY) sw = exp2f(floorf(log2f(32768.f / m)));
+            *w_scale = sw;
+            *inv_scale = 1.f / (sw * act_scale);
+        }
     }
 }
 __global__ void pack_split_kernel(const float* __restrict__ src, __half* __restrict__ hi,

@@ -41,7 +41,7 @@ template <int BN, int CG = 1> struct UmmaCfg {
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
     static constexpr int TMEM_COLS = 2 * BN;                    // double-buffered accumulator
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * 4096 /*epilogue staging*/ + 1024 /*align slack*/ +
-                                      128 /*barriers*/ + 1024 /*LN row stats*/;
+                                      192 /*barriers, seed slot*/ + 1024 /*LN row stats*/;
 };
 
 namespace ptx {
@@ -270,12 +270,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     uint64_t* rfull_bar = bars + 2 * STAGES + 5;  //           LN: residual tile landed in the ring (TMA -> epilogue)
-    float* row_stat = reinterpret_cast<float*>(bars + 2 * STAGES + 6);   // LN: [2 halves][128 rows] partials, then mean/rstd
+    float* row_stat = reinterpret_cast<float*>(bars + 2 * STAGES + 7);   // LN: [2 halves][128 rows] partials, then mean/rstd
     // LN fast path (no dropout): after a tile's last k-block the operand ring is idle, so the producer parks the
     // residual tile there (128 KB, the same 64-column swizzled boxes the GEMMs read xa / xb with) and the
     // epilogue stages its output boxes in the ring's last 64 KB; both stages go back to the producer when the
     // tile's epilogue is done.
-    const bool ln_ring = LN && !(ep.drop_p > 0.f);
+    const bool ln_ring = LN;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (N + BN - 1) / BN;
@@ -405,6 +405,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         const float asc = ep.acc_scale ? __ldg(ep.acc_scale) : 1.f;    // 1 / (s_a * s_w), a power of two
         const float osc = OUT_HALF ? ACT_SCALE : 1.f;             // output planes hold ACT_SCALE * x
         const float relu_floor = ep.relu ? 0.f : -INFINITY;
+        // dropout on the GEMM output (element index = row * N + col): threshold and scale are kernel parameters
+        // (constant bank, no registers), the site seed is parked in shared memory by the first epilogue thread --
+        // the LayerNorm epilogue holds a 128-column row in registers and has none to spare
+        volatile uint64_t* seed_slot = reinterpret_cast<volatile uint64_t*>(bars + 2 * STAGES + 6);
         int it = 0;
         for (int tile = grp; tile < total_tiles; tile += n_grp, ++it) {
             const int as = it & 1;
@@ -418,6 +422,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                 // the kernel leaves ~3 KB of L1, so a __ldg in the chunk loop is an exposed L2 round trip
                 const int et = (int)threadIdx.x - 64;
                 if (et < BN) row_stat[(it & 1) * 256 + et] = (n0 + et < N) ? __ldg(ep.bias + n0 + et) * osc : 0.f;
+                if (it == 0 && et == 0) *seed_slot = ep.drop_thr ? site_seed(ep.seed_ptr, ep.seed) : 0ull;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             ptx::mbar_wait(&tfull_bar[as], aphase);
@@ -426,7 +431,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
             const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
             float v[32];
             if constexpr (!LN) {
-                if (ep.tma_out && (n0 + BN <= N) && !(ep.drop_p > 0.f) && !(ep.dbg & 7)) {
+                if (ep.tma_out && (n0 + BN <= N) && !(ep.dbg & 7)) {
                     // thread = accumulator row: bias/ReLU/split in registers, 32x32 output box through a
                     // swizzled 4 KB shared tile, written to global by TMA (no transposition, no LSU stores)
                     const float sc = asc * osc;
@@ -443,6 +448,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                             v[4 * j4 + 1] = fmaxf(fmaf(v[4 * j4 + 1], sc, b.y), relu_floor);
                             v[4 * j4 + 2] = fmaxf(fmaf(v[4 * j4 + 2], sc, b.z), relu_floor);
                             v[4 * j4 + 3] = fmaxf(fmaf(v[4 * j4 + 3], sc, b.w), relu_floor);
+                        }
+                        if (ep.drop_thr) {                            // reference: dropout(relu(linear1(x))) -- warp-uniform branch
+                            const uint64_t g0 = ((uint64_t)(rbase + lane) * N + colb) >> 2;
+                            const uint64_t dseed = *seed_slot;
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 f = dropout_factor4(dseed, g0 + j4, ep.drop_thr, ep.drop_inv);
+                                v[4 * j4 + 0] *= f.x; v[4 * j4 + 1] *= f.y; v[4 * j4 + 2] *= f.z; v[4 * j4 + 3] *= f.w;
+                            }
                         }
                         if constexpr (OUT_HALF) {
                             // two [32 rows][64 B] tiles (hi, lo), 64B-swizzled: chunk ^= (row >> 1) & 3.  The two planes are
@@ -552,7 +566,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                         __syncwarp();
                     }
                 } else {
-                    const float inv_keep = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
+                    const float inv_keep = ep.drop_inv;
+                    const uint64_t dseed = *seed_slot;
 #pragma unroll 1
                     for (int c = 0; c < CH; ++c) {
                         const int colb = n0 + half * (BN / 2) + c * 32;     // first column of the chunk
@@ -571,7 +586,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                                 if (row < M && col + q < N && !(ep.dbg & 1)) {
                                     float x = fmaf(xs[q], asc, (ep.dbg & 2) ? 0.f : __ldg(ep.bias + col + q));
                                     x = fmaxf(x, relu_floor);
-                                    if (ep.drop_p > 0.f) x *= dropout_factor(ep.drop_p, inv_keep, ep.seed, (uint64_t)row * N + col + q);
+                                    if (ep.drop_p > 0.f) x *= dropout_factor(ep.drop_p, inv_keep, dseed, (uint64_t)row * N + col + q);
                                     const size_t off = (size_t)row * ep.ldc + col + q;
                                     if constexpr (OUT_HALF) {
                                         __half hi, lo;
@@ -601,6 +616,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                         cvec[t] = __ldg(ep.bias + t);
                         cvec[256 + t] = __ldg(ep.gamma + t) * ACT_SCALE;
                         cvec[512 + t] = __ldg(ep.beta + t) * ACT_SCALE;
+                        if (t == 0) *seed_slot = ep.drop_thr ? site_seed(ep.seed_ptr, ep.seed) : 0ull;
                         asm volatile("bar.sync 1, 256;" ::: "memory");
                     }
                     const int trow = quarter * 32 + lane;             // row within the tile
@@ -632,13 +648,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                             const float4 b0 = *reinterpret_cast<const float4*>(cvec + col0 + c * 32 + i * 8);       // broadcast
                             const float4 b1 = *reinterpret_cast<const float4*>(cvec + col0 + c * 32 + i * 8 + 4);
                             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                            // dropout1 / dropout2 of the encoder layer: on the sub-layer output, before the residual add
+                            // (one hash per four columns; dthr == 0: nothing is dropped and dinv == 1)
+                            const uint64_t g0 = ((uint64_t)(m0 + trow) * N + col0 + c * 32 + i * 8) >> 2;
 #pragma unroll
                             for (int q2 = 0; q2 < 4; ++q2) {
+                                uint32_t hbits = 0xFFFFFFFFu;
+                                if (ep.drop_thr) {                    // warp-uniform
+                                    const uint64_t h = hash_u64(*seed_slot, g0 + (q2 >> 1));
+                                    hbits = (q2 & 1) ? (uint32_t)(h >> 32) : (uint32_t)h;
+                                }
+                                const float f0 = (hbits & 0xFFFFu) < ep.drop_thr ? 0.f : ep.drop_inv;
+                                const float f1 = (hbits >> 16) < ep.drop_thr ? 0.f : ep.drop_inv;
                                 const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[q2]));
                                 const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[q2]));
                                 const int j = c * 32 + i * 8 + q2 * 2;
-                                const float v0 = fmaf(hf.x + lf.x, 1.f / ACT_SCALE, fmaf(x[j], asc, bb[q2 * 2]));
-                                const float v1 = fmaf(hf.y + lf.y, 1.f / ACT_SCALE, fmaf(x[j + 1], asc, bb[q2 * 2 + 1]));
+                                const float v0 = fmaf(hf.x + lf.x, 1.f / ACT_SCALE, fmaf(x[j], asc, bb[q2 * 2]) * f0);
+                                const float v1 = fmaf(hf.y + lf.y, 1.f / ACT_SCALE, fmaf(x[j + 1], asc, bb[q2 * 2 + 1]) * f1);
                                 x[j] = v0; x[j + 1] = v1;
                                 rsum += v0 + v1;
                             }
@@ -707,109 +733,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                     }
                     continue;                                         // tempty already arrived
                 }
-                const float inv_keep = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
-                const __half* res_hi = reinterpret_cast<const __half*>(ep.resid);
-                const __half* res_lo = reinterpret_cast<const __half*>(ep.resid_lo);
-                // ---- pass 1: x -> back to TMEM; row sums ----
-                float rsum = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < CH; ++c) {
-                    const int col = half * (BN / 2) + c * 32 + cchunk * 4;
-                    // residual of this lane's 8 rows first: its latency overlaps the TMEM load + staging
-                    uint2 rh[8], rl[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const size_t e = (size_t)min(rbase + i * 4 + crow, M - 1) * ep.ldr + col;
-                        rh[i] = __ldg(reinterpret_cast<const uint2*>(res_hi + e));
-                        rl[i] = __ldg(reinterpret_cast<const uint2*>(res_lo + e));
-                    }
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-                    ptx::tmem_ld32(t_acc + c * 32, v);
-                    stg_write_row(stg, lane, v);
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = i * 4 + crow;
-                        float4 x = *stg_ptr(stg, r, cchunk);
-                        x.x = fmaf(x.x, asc, b4.x); x.y = fmaf(x.y, asc, b4.y); x.z = fmaf(x.z, asc, b4.z); x.w = fmaf(x.w, asc, b4.w);
-                        if (!fast && ep.drop_p > 0.f) {
-                            const uint64_t id = (uint64_t)(rbase + r) * N + col;
-                            x.x *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id);
-                            x.y *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 1);
-                            x.z *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 2);
-                            x.w *= dropout_factor(ep.drop_p, inv_keep, ep.seed, id + 3);
-                        }
-                        const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&rh[i].x));
-                        const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&rh[i].y));
-                        const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&rl[i].x));
-                        const float2 l1 = __half22float2(*reinterpret_cast<const __half2*>(&rl[i].y));
-                        x.x = fmaf(h0.x + l0.x, 1.f / ACT_SCALE, x.x); x.y = fmaf(h0.y + l0.y, 1.f / ACT_SCALE, x.y);
-                        x.z = fmaf(h1.x + l1.x, 1.f / ACT_SCALE, x.z); x.w = fmaf(h1.y + l1.y, 1.f / ACT_SCALE, x.w);
-                        *stg_ptr(stg, r, cchunk) = x;
-                    }
-                    __syncwarp();
-                    stg_read_row(stg, lane, v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) rsum += v[j];
-                    ptx::tmem_st32(t_acc + c * 32, v);
-                    __syncwarp();
-                }
-                if (warp == 2 && it == 0) TIP_TS(4);
-                row_stat[half * 128 + quarter * 32 + lane] = rsum;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const float mean = (row_stat[quarter * 32 + lane] + row_stat[128 + quarter * 32 + lane]) * (1.f / BN);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                // ---- pass 2: centred second moment (thread = row, straight from TMEM) ----
-                float q2 = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < CH; ++c) {
-                    ptx::tmem_ld32(t_acc + c * 32, v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; q2 = fmaf(d, d, q2); }
-                }
-                if (warp == 2 && it == 0) TIP_TS(5);
-                row_stat[half * 128 + quarter * 32 + lane] = q2;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const float var = (row_stat[quarter * 32 + lane] + row_stat[128 + quarter * 32 + lane]) * (1.f / BN);
-                const float rstd = rsqrtf(var + 1e-5f);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                // scale / shift of the rows this lane touches in the "coal" pattern: y = x*a + b with
-                // a = rstd, b = -mean*rstd (then the per-column affine), all pre-multiplied by ACT_SCALE
-                float ca[8], cb[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float mu = __shfl_sync(0xffffffffu, mean, i * 4 + crow);
-                    const float rs = __shfl_sync(0xffffffffu, rstd, i * 4 + crow);
-                    ca[i] = rs;
-                    cb[i] = -mu * rs;
-                }
-                // ---- pass 3: normalise, affine, split, coalesced store ----
-#pragma unroll 1
-                for (int c = 0; c < CH; ++c) {
-                    const int col = half * (BN / 2) + c * 32 + cchunk * 4;
-                    float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + col));
-                    float4 e4 = __ldg(reinterpret_cast<const float4*>(ep.beta + col));
-                    g4.x *= ACT_SCALE; g4.y *= ACT_SCALE; g4.z *= ACT_SCALE; g4.w *= ACT_SCALE;
-                    e4.x *= ACT_SCALE; e4.y *= ACT_SCALE; e4.z *= ACT_SCALE; e4.w *= ACT_SCALE;
-                    ptx::tmem_ld32(t_acc + c * 32, v);
-                    stg_write_row(stg, lane, v);
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = i * 4 + crow, row = rbase + r;
-                        float4 x = *stg_ptr(stg, r, cchunk);
-                        x.x = fmaf(fmaf(x.x, ca[i], cb[i]), g4.x, e4.x);
-                        x.y = fmaf(fmaf(x.y, ca[i], cb[i]), g4.y, e4.y);
-                        x.z = fmaf(fmaf(x.z, ca[i], cb[i]), g4.z, e4.z);
-                        x.w = fmaf(fmaf(x.w, ca[i], cb[i]), g4.w, e4.w);
-                        if (row < M) {
-                            const size_t off = (size_t)row * ep.ldc + col;
-                            half_split_store4_fast(reinterpret_cast<__half*>(ep.out) + off,
-                                                   reinterpret_cast<__half*>(ep.out_lo) + off, x);
-                        }
-                    }
-                    __syncwarp();
-                }
+                // (the LayerNorm epilogue always takes the ring path above)
             }
             if (warp == 2 && it == 0) TIP_TS(6);
             ptx::tc_fence_before();

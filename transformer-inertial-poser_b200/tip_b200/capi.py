@@ -38,11 +38,10 @@ SIGNATURES = {
     "tip_abi_version": (C.c_int, []),
     "tip_create": (C.c_int, [C.POINTER(TipDims), C.POINTER(_VP)]),
     "tip_destroy": (None, [_VP]),
+    "tip_create_lane": (C.c_int, [_VP, C.POINTER(_VP)]),
     "tip_last_error": (C.c_char_p, [_VP]),
     "tip_num_weight_tensors": (C.c_int, [_VP]),
     "tip_pack_weights": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(C.c_int64), C.c_int, _VP]),
-    "tip_packed_blob": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(C.c_size_t)]),
-    "tip_mark_packed": (C.c_int, [_VP]),
     "tip_forward": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP, C.c_float,
                               C.POINTER(TipDropout), _VP]),
     "tip_forward_host": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int,
@@ -89,7 +88,7 @@ def load_library(path: str | None = None):
         fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.tip_abi_version() != 1:
+    if lib.tip_abi_version() != 2:
         raise RuntimeError("tip_b200: ABI version mismatch between capi.py and libtip_b200.so")
     if path is None:
         _lib = lib

@@ -124,6 +124,8 @@ class TF_RNN_Past_State(nn.Module):
         self._packed_sig = None
         self._packed_versions = None
         self._plist = None
+        self._owner = None          # lanes: the module whose packed weights this handle shares
+        self._owner_handle = None
 
     # -------------------------------------------------------------------------------------------
     def _ordered_params(self):
@@ -153,6 +155,17 @@ class TF_RNN_Past_State(nn.Module):
         the signature, a bare ``param.data = tensor`` is picked up by the next full check (any ``forward``)."""
         if self._lib is None:
             self._lib = capi.load_library()
+        if self._owner is not None:
+            # a lane: the owner packs (once, for all lanes); this handle shares its packed weights (tip_create_lane)
+            oh = self._owner._ensure(device, fast=fast)
+            if self._handle is None or self._device != device or self._owner_handle != oh.value:
+                self._release()
+                with torch.cuda.device(device):
+                    h = C.c_void_p()
+                    rc = self._lib.tip_create_lane(oh, C.byref(h))
+                    capi.check(self._lib, None, rc, "tip_create_lane")
+                self._handle, self._device, self._owner_handle = h, device, oh.value
+            return self._handle
         if self._handle is None or self._device != device:
             self._release()
             with torch.cuda.device(device):
@@ -247,8 +260,9 @@ class TF_RNN_Past_State(nn.Module):
     # ---- extras beyond the reference surface --------------------------------------------------
     def make_lane(self):
         """A second execution lane: a module that SHARES this module's Parameter objects (no copy; a
-        ``load_state_dict`` / optimiser step / ``.cuda()`` on either is seen by both) but owns its own C
-        handle, i.e. its own packed weights, workspace, captured graphs and job slots.  Forwards of
+        ``load_state_dict`` / optimiser step / ``.cuda()`` on either is seen by both) and its PACKED weights
+        (``tip_create_lane``: one packed copy per GPU, packed once) but owns its own C handle, i.e. its own
+        workspace, captured graphs and job slots.  Forwards of
         different lanes may run concurrently on different CUDA streams -- the LayerNorm GEMMs (80 row
         tiles at B = 256) and the recurrence (104 SMs) leave SMs idle that another lane's kernels fill:
         two lanes give 598 k instead of 498 k frames/s at B = 256.  Dropout settings and train/eval mode
@@ -265,6 +279,9 @@ class TF_RNN_Past_State(nn.Module):
         lane.training = self.training
         lane._lib = self._lib
         lane._handle = lane._device = lane._packed_sig = lane._packed_versions = lane._plist = None
+        # (plain attribute, not a registered sub-module: the lane's state_dict stays the reference's 56 keys)
+        object.__setattr__(lane, "_owner", self if self._owner is None else self._owner)
+        lane._owner_handle = None
         return lane
 
     def _sync_lane_settings(self, src):
