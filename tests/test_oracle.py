@@ -184,7 +184,7 @@ def test_product_synthetic_generators_match_the_oracle_copies():
 
 def test_bench_reference_arm_runs_on_cpu_and_prints_one_json_line():
     """`bench.py --impl reference` (the driver's reference arm) needs no GPU: one JSON line on stdout with the
-    contract's keys, timed on the CPU torch port."""
+    contract's keys, timed on the UNMODIFIED reference module when the install is staged (else the torch port)."""
     import json
     import subprocess
     import sys
@@ -197,7 +197,9 @@ def test_bench_reference_arm_runs_on_cpu_and_prints_one_json_line():
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["metric"] == "imu_frames_per_sec_seq40_6imu" and j["unit"] == "frames/s"
     assert j["higher_is_better"] is True and j["value"] > 0 and j["n_gpus"] == 1
-    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    staged = os.path.exists(os.path.join(root, "baseline", "_ref", "reference", "simple_transformer_with_state.py"))
+    assert j["cpu_baseline"]["kind"] == ("reference" if staged else "port") and j["cpu_baseline"]["cores"] >= 1
+    assert "BASELINE configs[1]" in j["config"]["workload"]
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
 
 

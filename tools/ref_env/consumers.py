@@ -20,8 +20,8 @@ The reference sources are read from the staged install ``baseline/_ref/reference
 * optionally the deterministic parity mode of SURVEY.md 8c (``eval()``, ``past_state_dropout = 0``), applied by
   wrapping the constructor of whichever class the consumer imports -- the consumers themselves leave the module
   in train mode with p = 0.8 (offline_testing_simple.py:93,98), which is the "as shipped" mode;
-* on a box without a GPU (the build container) ``Tensor.cuda`` / ``Module.cuda`` become the identity so that the
-  REFERENCE model runs on the CPU; the drop-in has no CPU path.
+* on a box without a GPU (the build container) ``Tensor.cuda`` / ``Module.cuda`` become the identity and
+  ``torch.load`` maps to the CPU, so that the REFERENCE model runs on the CPU; the drop-in has no CPU path.
 
 Test / bench infrastructure: the product never imports this file.
 """
@@ -101,7 +101,7 @@ def consumer_env(dropin: bool, deterministic: bool = False, workdir: str | None 
     if ref is None:
         raise RuntimeError("reference sources are not staged (baseline/_ref/reference); run __graft_entry__.build() in the build container")
     saved_path, saved_cwd = list(sys.path), os.getcwd()
-    saved_cuda = (torch.Tensor.cuda, torch.nn.Module.cuda)
+    saved_cuda = (torch.Tensor.cuda, torch.nn.Module.cuda, torch.load)
     _purge()
     model_dir = PKG if dropin else ref
     sys.path[:] = [model_dir, SHIMS, ref] + [p for p in saved_path if p not in (model_dir, SHIMS, ref, PKG)] + ([PKG] if not dropin else [])
@@ -114,6 +114,9 @@ def consumer_env(dropin: bool, deterministic: bool = False, workdir: str | None 
         if cpu_reference:
             torch.Tensor.cuda = lambda self, *a, **k: self
             torch.nn.Module.cuda = lambda self, *a, **k: self
+            _load = saved_cuda[2]
+            # (the released checkpoints hold CUDA tensors; offline_testing_simple.py:96 loads them without map_location)
+            torch.load = lambda f, *a, **k: _load(f, *a, **{**k, "map_location": k.get("map_location", "cpu")})
         os.chdir(workdir or ref)
         import simple_transformer_with_state as stws
         expect = os.path.realpath(os.path.join(model_dir, "simple_transformer_with_state.py"))
@@ -133,7 +136,7 @@ def consumer_env(dropin: bool, deterministic: bool = False, workdir: str | None 
             if deterministic:
                 cls.__init__ = orig_init
     finally:
-        torch.Tensor.cuda, torch.nn.Module.cuda = saved_cuda
+        torch.Tensor.cuda, torch.nn.Module.cuda, torch.load = saved_cuda
         os.chdir(saved_cwd)
         sys.path[:] = saved_path
         _purge()
@@ -274,7 +277,9 @@ def run_offline_testing_simple(dropin: bool, workdir: str, deterministic: bool, 
             pass
     names = ["joint_angle_err_deg", "joint_pos_err_cm", "root_drift_2s_m", "root_drift_5s_m", "root_drift_10s_m",
              "jerk_all", "jerk_root"]
-    return {"metrics": dict(zip(names, nums[:7])), "ours_list": dump["ours_list"], "gt_list": dump["gt_list"],
+    # (the script prints the file count first, then the 7 means, then 7 "max <file>" lines)
+    assert len(nums) >= 7, text[-2000:]
+    return {"metrics": dict(zip(names, nums[-7:])), "ours_list": dump["ours_list"], "gt_list": dump["gt_list"],
             "stdout": text}
 
 

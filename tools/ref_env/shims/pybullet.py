@@ -281,7 +281,26 @@ def createCollisionShape(*a, **kw):
     return -1
 
 
-def createMultiBody(*a, **kw):
+class _Marker:
+    """A free body without links (the SBP marker spheres of render_funcs.py:213-225): only its base pose is kept."""
+    n = 0
+
+    def __init__(self, pos, orn):
+        self.base_p = np.asarray(pos, dtype=float)
+        self.base_Q = np.asarray(orn, dtype=float)
+        self.base_v = np.zeros(3)
+        self.base_w = np.zeros(3)
+
+
+def createMultiBody(baseMass=0.0, baseCollisionShapeIndex=-1, baseVisualShapeIndex=-1, basePosition=(0, 0, 0),
+                    baseOrientation=(0, 0, 0, 1), *a, **kw):
+    bid = _next_body[0]
+    _next_body[0] += 1
+    _bodies[bid] = _Marker(basePosition, baseOrientation)
+    return bid
+
+
+def loadTexture(*a, **kw):
     return -1
 
 

@@ -40,7 +40,7 @@ struct FwdGraph {
     int launches = 0;
     uint64_t last_use = 0;
 };
-constexpr int FWD_GRAPH_SLOTS = 32;     // captured forwards kept per handle (LRU); a lane rotating 16 input sets needs 16
+constexpr int FWD_GRAPH_SLOTS = 64;     // captured forwards kept per handle (LRU); a lane rotating 16 input sets in two dropout modes needs 32
 
 // Packed weights: owned by the handle tip_create made, shared (read-only) by the lanes tip_create_lane derives from it.
 struct SharedWeights {

@@ -84,9 +84,11 @@ class HostPipeline:
     that many execution lanes, whose forwards overlap on the GPU (``depth`` >= 2 * lanes keeps every lane's
     copies hidden under its forwards)."""
 
-    def __init__(self, model, depth: int = 2, last_row_only: bool = False, lanes: int = 1):
+    def __init__(self, model, depth: int = 2, last_row_only: bool = False, lanes: int = 1, lane_models=None):
         self.model = model
-        self.models = _lanes_of(model, lanes)
+        # lane_models: re-use existing lanes (e.g. ``ForwardLanes.models``) instead of creating new handles
+        self.models = list(lane_models) if lane_models is not None else _lanes_of(model, lanes)
+        lanes = len(self.models)
         per_lane = -(-depth // lanes)
         if depth < 1 or per_lane > capi.TIP_HOST_SLOTS:
             raise ValueError(f"depth must be in 1..{capi.TIP_HOST_SLOTS * lanes} for {lanes} lane(s)")
