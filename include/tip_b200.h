@@ -73,7 +73,9 @@ typedef struct tip_dropout {
  * kept elements are scaled by 1/(1-p).  Sites and element indices (rows are b*L + t, batch-global):
  *   x_imu (:73)  site 0x1111, idx = row * kin_pad + c            (c = column of the concatenated input row,
  *   x_s   (:77)  site 0x2222, idx = row * kin_pad + n_imu + c     kin_pad = (n_imu + size_s) rounded up to 64)
- *   layer l (0-based): attention probabilities 101*(l+1), idx = ((b*16 + h)*40 + query)*40 + key;
+ *   layer l (0-based): attention probabilities 101*(l+1), idx = 4*group + lane with bh = b*16 + h,
+ *     group = ((bh*3 + query/16)*8 + query%8)*20 + key/2, lane = 2*((query%16)/8) + key%2 (the four probabilities one
+ *     lane of the tensor-core kernel holds -- rows r, r+8 of a 16-row tile x two adjacent keys -- share one hash);
  *   dropout1 (on out_proj, before the residual) 211*(l+1), idx = row*256 + col;  FFN inner dropout (after ReLU)
  *   307*(l+1), idx = row*1024 + col;  dropout2 (on linear2) 401*(l+1), idx = row*256 + col.
  * Batches of more than 1024 windows are processed in chunks of 1024; chunk k adds k * 0x632BE59BD9B4E019 to the

@@ -158,6 +158,17 @@ def dropout_factors(seed, idx, p, dtype=np.float32):
     return np.where(u < np.uint64(thr), np.float32(0.0), inv).astype(dtype)
 
 
+def attn_drop_index(B, n_heads, L):
+    """Element indices (B, H, L, L) of the attention-probability dropout (tip_common.cuh attn_drop_index): queries r
+    and r + 8 of a 16-row tile x two adjacent keys share one hash group."""
+    u = np.uint64
+    bh = (np.arange(B, dtype=u)[:, None] * u(n_heads) + np.arange(n_heads, dtype=u))[:, :, None, None]
+    q = np.arange(L, dtype=u)[None, None, :, None]
+    k = np.arange(L, dtype=u)[None, None, None, :]
+    grp = ((bh * u(3) + (q >> u(4))) * u(8) + (q & u(7))) * u(20) + (k >> u(1))
+    return u(4) * grp + (u(2) * ((q >> u(3)) & u(1)) + (k & u(1)))
+
+
 def forward(sd, x_imu, x_s, n_heads=16, with_rnn=True, keep_mask=None, past_scale=1.0,
             dtype=np.float32, return_intermediates=False, dropout=None):
     """Restatement of TF_RNN_Past_State.forward: deterministic (``dropout=None``), or as shipped with the
@@ -218,9 +229,7 @@ def forward(sd, x_imu, x_s, n_heads=16, with_rnn=True, keep_mask=None, past_scal
         pr = np.exp(s)
         pr = pr / pr.sum(axis=-1, keepdims=True)
         if p_enc > 0:                                               # attention-probability dropout
-            bh = (np.arange(B, dtype=np.uint64)[:, None] * np.uint64(n_heads) + np.arange(n_heads, dtype=np.uint64))
-            idx = ((bh[:, :, None] * np.uint64(40) + np.arange(L, dtype=np.uint64)[None, None, :])[..., None] * np.uint64(40)
-                   + np.arange(L, dtype=np.uint64))
+            idx = attn_drop_index(B, n_heads, L)
             pr = pr * dropout_factors(seed + seed_attn(i), idx, p_enc, dtype)
         o = (pr @ v).transpose(0, 2, 1, 3).reshape(B, L, E)
         a = o @ W[p + "self_attn.out_proj.weight"].T + W[p + "self_attn.out_proj.bias"]

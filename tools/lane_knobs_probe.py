@@ -8,6 +8,8 @@ sd, _ = load_weights()
 dev = torch.device('cuda:0')
 B = int(os.environ.get('B', '256')); N = int(os.environ.get('N', '192')); NS = 16
 model = build_model(sd, dev)
+if os.environ.get('MODE') == 'as_shipped':      # the consumers' default: train mode, fresh Dropout(0.8) per call
+    model.train(); model.past_state_dropout = 0.8
 sets = []
 for i in range(NS):
     xi, xs = synth(1 + 1000 * i, B)

@@ -6,6 +6,8 @@ sd, _ = load_weights()
 m = build_model(sd, torch.device('cuda:0'))
 import os
 if os.environ.get('ENGINE'): m.set_gemm_engine(int(os.environ['ENGINE']))
+if os.environ.get('MODE') == 'as_shipped':
+    m.train(); m.past_state_dropout = 0.8
 m.set_profile(True)
 for B in [int(b) for b in os.environ.get('BS','1,8,16,64,128,256,512').split(',')]:
     xi, xs = synth(1, B)

@@ -141,20 +141,17 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
         }
         ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1)); ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
         mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
-        // exp, row sums (fp32, before dropout), optional attention dropout.  Element index of P[b, h, query, key] =
-        // ((b * 16 + h) * 40 + query) * 40 + key: this lane's two keys of a tile (2*t4, 2*t4 + 1) share one hash group
+        // exp, row sums (fp32, before dropout), optional attention dropout (element index: attn_drop_index)
         float la = 0.f, lb = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 6; ++nt) {
             if (!(nt <= 2 * mt + 1 && nt < 5)) continue;         // s[nt] stays 0 there: contributes nothing to P V
             float fa[2] = {1.f, 1.f}, fb[2] = {1.f, 1.f};
             if (drop_p > 0.f) {
-                const int key0 = 8 * nt + 2 * t4;
-                const uint64_t ida = (((uint64_t)(b0 + b) * NH + h0 + hl) * MAXL + ra) * MAXL + key0;
-                const uint64_t idb = (((uint64_t)(b0 + b) * NH + h0 + hl) * MAXL + rb) * MAXL + key0;
-                const float4 a4 = dropout_factor4(seed, ida >> 2, dthr, inv_keep), b4 = dropout_factor4(seed, idb >> 2, dthr, inv_keep);
-                if (ida & 2) { fa[0] = a4.z; fa[1] = a4.w; } else { fa[0] = a4.x; fa[1] = a4.y; }
-                if (idb & 2) { fb[0] = b4.z; fb[1] = b4.w; } else { fb[0] = b4.x; fb[1] = b4.y; }
+                // this lane's four probabilities of the tile (rows ra, rb = ra + 8; keys key0, key0 + 1) = one hash group
+                const uint64_t grp = attn_drop_index((uint64_t)(b0 + b) * NH + h0 + hl, ra, 8 * nt + 2 * t4) >> 2;
+                const float4 f4 = dropout_factor4(seed, grp, dthr, inv_keep);
+                fa[0] = f4.x; fa[1] = f4.y; fb[0] = f4.z; fb[1] = f4.w;
             }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {

@@ -86,6 +86,14 @@ __device__ __forceinline__ float dropout_factor(float p, float inv_keep, uint64_
     const uint32_t u = (uint32_t)(h >> (16 * (idx & 3))) & 0xFFFFu;
     return u < drop_threshold(p) ? 0.f : inv_keep;
 }
+// Element index of the attention-probability dropout, P[bh = b * 16 + h][query][key]: the four probabilities one lane
+// of the tensor-core attention kernel holds per key tile -- queries r and r + 8 of a 16-row tile x two adjacent keys --
+// form ONE hash group (one hash per four probabilities): group = ((bh * 3 + query / 16) * 8 + query % 8) * 20 + key / 2,
+// lane = 2 * ((query % 16) / 8) + key % 2.
+__host__ __device__ __forceinline__ uint64_t attn_drop_index(uint64_t bh, int query, int key) {
+    const uint64_t grp = ((bh * 3 + (uint64_t)(query >> 4)) * 8 + (uint64_t)(query & 7)) * 20 + (uint64_t)(key >> 1);
+    return 4 * grp + (uint64_t)(2 * ((query >> 3) & 1) + (key & 1));
+}
 // site seed = *base (device memory; null = 0) + per-site offset
 __device__ __forceinline__ uint64_t site_seed(const uint64_t* base, uint64_t off) { return (base ? *base : 0ull) + off; }
 // per-site offsets (layer l = 0..): also restated in oracle/tip_oracle.py

@@ -365,8 +365,8 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* 
             la += pa;
             lb += pb;
             if (drop_p > 0.f) {   // attention-probability dropout (train mode only)
-                const uint64_t ida = (((uint64_t)(b0 + b) * NH + h0 + hl) * MAXL + ra) * MAXL + j;
-                const uint64_t idb = (((uint64_t)(b0 + b) * NH + h0 + hl) * MAXL + rb) * MAXL + j;
+                const uint64_t ida = attn_drop_index((uint64_t)(b0 + b) * NH + h0 + hl, ra, j);
+                const uint64_t idb = attn_drop_index((uint64_t)(b0 + b) * NH + h0 + hl, rb, j);
                 pa *= dropout_factor(drop_p, inv_keep, seed, ida);
                 pb *= dropout_factor(drop_p, inv_keep, seed, idb);
             }

@@ -246,7 +246,9 @@ __device__ __forceinline__ void half_split_store4_fast(__half* hi_p, __half* lo_
 constexpr int UM_EPI_WARPS = 8;                 // two warps per TMEM lane quarter (column halves)
 constexpr int UM_THREADS = 64 + 32 * UM_EPI_WARPS;
 
-template <int BN, bool LN, bool OUT_HALF, int CG = 1>
+// DROP (LayerNorm variant only): dropout1 / dropout2 compiled in.  The LayerNorm epilogue is issue-bound, so the
+// deterministic kernel carries none of the mask arithmetic (the non-LN kernels take a warp-uniform branch instead).
+template <int BN, bool LN, bool OUT_HALF, int CG = 1, bool DROP = false>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                  const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
@@ -256,7 +258,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     const bool pdl_early = ep.pdl_early != 0;
     using Cfg = UmmaCfg<BN, CG>;
     constexpr int STAGES = Cfg::STAGES;
-    static_assert(CG == 1 || (CG == 2 && !LN && BN == 256), "pair tiles: 256 x 256, no LayerNorm epilogue");
+    static_assert(CG == 1 || (CG == 2 && !LN && (BN == 256 || BN == 128)), "pair tiles: 256 x 256 or 256 x 128, no LayerNorm epilogue");
     // 128B-swizzled operand tiles need 1024-byte alignment.  The kernel has no static shared memory,
     // so the dynamic window starts at shared offset 0; keeping the pointer un-cast preserves the
     // shared address space (LDS/STS instead of generic LD/ST for the epilogue staging).
@@ -270,7 +272,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     uint64_t* rfull_bar = bars + 2 * STAGES + 5;  //           LN: residual tile landed in the ring (TMA -> epilogue)
-    float* row_stat = reinterpret_cast<float*>(bars + 2 * STAGES + 7);   // LN: [2 halves][128 rows] partials, then mean/rstd
+    float* row_stat = reinterpret_cast<float*>(bars + 2 * STAGES + 8);   // (16-byte aligned: float4 reads)   // LN: [2 halves][128 rows] partials, then mean/rstd
     // LN fast path (no dropout): after a tile's last k-block the operand ring is idle, so the producer parks the
     // residual tile there (128 KB, the same 64-column swizzled boxes the GEMMs read xa / xb with) and the
     // epilogue stages its output boxes in the ring's last 64 KB; both stages go back to the producer when the
@@ -613,7 +615,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                     float* cvec = staging;                            // [0,256) bias, [256,512) gamma*16, [512,768) beta*16
                     if (it == 0) {
                         const int t = (int)threadIdx.x - 64;          // 0..255 among the epilogue threads
-                        cvec[t] = __ldg(ep.bias + t);
+                        cvec[t] = __ldg(ep.bias + t) * (DROP ? ep.drop_inv : 1.f);       // kept elements carry 1/(1-p)
                         cvec[256 + t] = __ldg(ep.gamma + t) * ACT_SCALE;
                         cvec[512 + t] = __ldg(ep.beta + t) * ACT_SCALE;
                         if (t == 0) *seed_slot = ep.drop_thr ? site_seed(ep.seed_ptr, ep.seed) : 0ull;
@@ -648,23 +650,30 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                             const float4 b0 = *reinterpret_cast<const float4*>(cvec + col0 + c * 32 + i * 8);       // broadcast
                             const float4 b1 = *reinterpret_cast<const float4*>(cvec + col0 + c * 32 + i * 8 + 4);
                             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                            // dropout1 / dropout2 of the encoder layer: on the sub-layer output, before the residual add
-                            // (one hash per four columns; dthr == 0: nothing is dropped and dinv == 1)
-                            const uint64_t g0 = ((uint64_t)(m0 + trow) * N + col0 + c * 32 + i * 8) >> 2;
+                            // dropout1 / dropout2 of the encoder layer (DROP): on the sub-layer output, before the residual
+                            // add.  One hash per four columns; element e of a group is dropped when its 16-bit lane of the
+                            // hash is below drop_thr; the kept ones carry 1/(1-p) through the pre-scaled asc / bias.
+                            uint32_t hw2[4] = {0u, 0u, 0u, 0u};
+                            if constexpr (DROP) {
+                                const uint64_t g0 = ((uint64_t)(m0 + trow) * N + col0 + c * 32 + i * 8) >> 2;
+                                const uint64_t sd = *seed_slot;
+                                const uint64_t ha = hash_u64(sd, g0), hb2 = hash_u64(sd, g0 + 1);
+                                hw2[0] = (uint32_t)ha; hw2[1] = (uint32_t)(ha >> 32); hw2[2] = (uint32_t)hb2; hw2[3] = (uint32_t)(hb2 >> 32);
+                            }
+                            const float ascd = DROP ? asc * ep.drop_inv : asc;
+                            const uint32_t thr_hi = ep.drop_thr << 16;
 #pragma unroll
                             for (int q2 = 0; q2 < 4; ++q2) {
-                                uint32_t hbits = 0xFFFFFFFFu;
-                                if (ep.drop_thr) {                    // warp-uniform
-                                    const uint64_t h = hash_u64(*seed_slot, g0 + (q2 >> 1));
-                                    hbits = (q2 & 1) ? (uint32_t)(h >> 32) : (uint32_t)h;
-                                }
-                                const float f0 = (hbits & 0xFFFFu) < ep.drop_thr ? 0.f : ep.drop_inv;
-                                const float f1 = (hbits >> 16) < ep.drop_thr ? 0.f : ep.drop_inv;
                                 const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[q2]));
                                 const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[q2]));
                                 const int j = c * 32 + i * 8 + q2 * 2;
-                                const float v0 = fmaf(hf.x + lf.x, 1.f / ACT_SCALE, fmaf(x[j], asc, bb[q2 * 2]) * f0);
-                                const float v1 = fmaf(hf.y + lf.y, 1.f / ACT_SCALE, fmaf(x[j + 1], asc, bb[q2 * 2 + 1]) * f1);
+                                float s0 = fmaf(x[j], ascd, bb[q2 * 2]), s1 = fmaf(x[j + 1], ascd, bb[q2 * 2 + 1]);
+                                if constexpr (DROP) {
+                                    if ((hw2[q2] << 16) < thr_hi) s0 = 0.f;          // lane 0: low 16 bits
+                                    if (hw2[q2] < thr_hi) s1 = 0.f;                  // lane 1: high 16 bits
+                                }
+                                const float v0 = fmaf(hf.x + lf.x, 1.f / ACT_SCALE, s0);
+                                const float v1 = fmaf(hf.y + lf.y, 1.f / ACT_SCALE, s1);
                                 x[j] = v0; x[j + 1] = v1;
                                 rsum += v0 + v1;
                             }
@@ -766,6 +775,7 @@ struct UmmaMaps {
     UmmaOperand w_in, w_qkv[MAX_LAYERS], w_o[MAX_LAYERS], w_1[MAX_LAYERS], w_2[MAX_LAYERS], w_ih, w_l;
     UmmaOperand w_qkv256[MAX_LAYERS], w_1256[MAX_LAYERS], w_ih256;        // 256-row boxes of the same planes (wide tiles)
     UmmaOperand w_o64[MAX_LAYERS], w_264[MAX_LAYERS];                     // 64-row boxes (skinny-M LayerNorm GEMMs, 4 CTAs per row tile)
+    UmmaOperand w_qkv64[MAX_LAYERS], w_164[MAX_LAYERS], w_ih64;           // 64-row boxes: each CTA of a 256 x 128 pair tile stages half of B
     UmmaOutput o_pre;                                                      // fp32 [rows][256] scratch of the un-fused LayerNorm path
     UmmaOutput o_xa, o_xb, o_hid, o_qkv, o_gi;                             // TMA-store targets
     UmmaOperand w_hh;                                                      // resident A operand of the recurrence (box 64 x 64)
@@ -863,10 +873,13 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         wgt(mp.w_o64[l], L.wo_hi, L.wo_lo, E, E, 64);
         wgt(mp.w_264[l], L.w2_hi, L.w2_lo, E, F, 64);
         wgt(mp.w_1256[l], L.w1_hi, L.w1_lo, F, E, 256);
+        wgt(mp.w_qkv64[l], L.wqkv_hi, L.wqkv_lo, 3 * E, E, 64);
+        wgt(mp.w_164[l], L.w1_hi, L.w1_lo, F, E, 64);
         wgt(mp.w_2[l], L.w2_hi, L.w2_lo, E, F, 256);
     }
     if (d.with_rnn) wgt(mp.w_ih, o.wih_hi, o.wih_lo, R, E, 128);
     if (d.with_rnn) wgt(mp.w_ih256, o.wih_hi, o.wih_lo, R, E, 256);
+    if (d.with_rnn) wgt(mp.w_ih64, o.wih_hi, o.wih_lo, R, E, 64);
     if (d.with_rnn) wgt(mp.w_hh, o.whh_hi, o.whh_lo, R, R, 16);     // 16-row boxes: hi/lo rows interleave per TMEM quarter
     wgt(mp.w_l, o.wl_hi, o.wl_lo, HEAD_NPAD, d.khead, 128);
     if (!ok) { err = "cuTensorMapEncodeTiled failed (driver entry point missing or bad tensor-map arguments)"; return TIP_ERR_CUDA; }
@@ -877,11 +890,14 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         cudaFuncSetAttribute(umma_gemm_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<256, true, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256, 2>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256, 2>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<128, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 2>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<128, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 2>::SMEM_BYTES);
         mp.attrs_set = true;
     }
     return TIP_OK;
@@ -891,7 +907,11 @@ inline bool wide_mode() {      // experiment: 128 x 256 single-CTA tiles (measur
     static const int v = getenv("TIP_BN256") ? atoi(getenv("TIP_BN256")) : 0;
     return v != 0;
 }
-inline bool pair_mode() {      // experiment (TIP_PAIR=1): CTA-pair tiles for the wide non-LN GEMMs.  Measured: the mainloop becomes MMA-bound (4.2 us per 256x256 tile) but the 128x256 epilogue per CTA (5 us) is then the critical path -> no gain over 128x128 single-CTA tiles
+inline int pair_kind() {       // TIP_PAIR: 1 = 256 x 256 pair tiles, 2 = 256 x 128 pair tiles (each CTA: its 128 rows of A, 64 rows of B)
+    static const int v = getenv("TIP_PAIR") ? atoi(getenv("TIP_PAIR")) : 0;
+    return v;
+}
+inline bool pair_mode_unused() {      // experiment (TIP_PAIR=1): CTA-pair tiles for the wide non-LN GEMMs.  Measured: the mainloop becomes MMA-bound (4.2 us per 256x256 tile) but the 128x256 epilogue per CTA (5 us) is then the critical path -> no gain over 128x128 single-CTA tiles
     static const int v = getenv("TIP_PAIR") ? atoi(getenv("TIP_PAIR")) : 0;
     return v != 0;
 }
@@ -901,15 +921,15 @@ inline bool pair_mode() {      // experiment (TIP_PAIR=1): CTA-pair tiles for th
 inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, const Epi& ep_in, bool ln,
                       cudaStream_t st, int m_tile0 = 0, int m_tile_cnt = -1, bool skinny = false) {
     pdl_kind() = 1;
-    const UmmaOperand *A = nullptr, *B = nullptr, *B256 = nullptr;
+    const UmmaOperand *A = nullptr, *B = nullptr, *B256 = nullptr, *B64 = nullptr;
     const UmmaOutput* C = nullptr;
     switch (which) {
         case UG_IN:     A = &mp.a_xin; B = &mp.w_in; C = &mp.o_xa; break;
-        case UG_QKV:    A = &mp.a_xa;  B = &mp.w_qkv[layer]; B256 = &mp.w_qkv256[layer]; C = &mp.o_qkv; break;
+        case UG_QKV:    A = &mp.a_xa;  B = &mp.w_qkv[layer]; B256 = &mp.w_qkv256[layer]; B64 = &mp.w_qkv64[layer]; C = &mp.o_qkv; break;
         case UG_OUT:    A = &mp.a_att; B = &mp.w_o[layer]; C = &mp.o_xb; break;
-        case UG_FF1:    A = &mp.a_xb;  B = &mp.w_1[layer]; B256 = &mp.w_1256[layer]; C = &mp.o_hid; break;
+        case UG_FF1:    A = &mp.a_xb;  B = &mp.w_1[layer]; B256 = &mp.w_1256[layer]; B64 = &mp.w_164[layer]; C = &mp.o_hid; break;
         case UG_FF2:    A = &mp.a_hid; B = &mp.w_2[layer]; C = &mp.o_xa; break;
-        case UG_IH:     A = &mp.a_xa;  B = &mp.w_ih; B256 = &mp.w_ih256; C = &mp.o_gi; break;
+        case UG_IH:     A = &mp.a_xa;  B = &mp.w_ih; B256 = &mp.w_ih256; B64 = &mp.w_ih64; C = &mp.o_gi; break;
         case UG_HEAD_R: A = &mp.a_hs;  B = &mp.w_l; break;      // y (ldc = size_s, unaligned): plain stores
         default:        A = &mp.a_xa;  B = &mp.w_l; break;      // UG_HEAD_E
     }
@@ -929,8 +949,30 @@ inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, c
     }
     if (ln) {
         const int tiles = m_tiles;                                // BN = 256 = the whole row
-        launch_k(umma_gemm_kernel<256, true, true>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<256>::SMEM_BYTES, st, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
-    } else if (B256 && (N % 256) == 0 && (m_tiles % 2) == 0 && (m_tiles / 2) * (N / 256) >= 32 && pair_mode()) {
+        if (ep.drop_thr)
+            launch_k(umma_gemm_kernel<256, true, true, 1, true>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<256>::SMEM_BYTES, st, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+        else
+            launch_k(umma_gemm_kernel<256, true, true>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<256>::SMEM_BYTES, st, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+    } else if (B64 && (N % 128) == 0 && (m_tiles % 2) == 0 && (m_tiles / 2) * (N / 128) >= 32 && pair_kind() == 2) {
+        // CTA pairs, 256 x 128 tiles: the pair's two CTAs stage their own 128 rows of A and 64 rows of B each -- 48 KB of
+        // operands per CTA per k-block instead of 64 KB -- and keep the 128 x 128 epilogue of the single-CTA tiles
+        const int units = (m_tiles / 2) * (N / 128);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * std::min(units, mp.num_sms / 2));
+        cfg.blockDim = dim3(UM_THREADS);
+        cfg.dynamicSmemBytes = UmmaCfg<128, 2>::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        if (ep.out_lo)
+            cudaLaunchKernelEx(&cfg, umma_gemm_kernel<128, false, true, 2>, A->hi, A->lo, B64->hi, B64->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+        else
+            cudaLaunchKernelEx(&cfg, umma_gemm_kernel<128, false, false, 2>, A->hi, A->lo, B64->hi, B64->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+    } else if (B256 && (N % 256) == 0 && (m_tiles % 2) == 0 && (m_tiles / 2) * (N / 256) >= 32 && pair_kind() == 1) {
         // CTA pairs (cta_group::2): 256 x 256 tiles, each CTA stages its 128 rows of A and half of B
         const int units = (m_tiles / 2) * (N / 256);
         cudaLaunchConfig_t cfg{};
