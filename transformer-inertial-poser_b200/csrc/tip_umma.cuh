@@ -33,13 +33,15 @@ constexpr int UM_BK = 64;           // fp16 elements per k-block = one 128-byte 
 // CG = CTAs per tile: 1 (M = 128, tcgen05 cta_group::1) or 2 (a CTA pair computes a 256 x BN tile with
 // cta_group::2 MMAs: each CTA stages its own 128 rows of A and HALF of the B tile, so the L2->SM operand
 // traffic per flop is half that of two independent CTAs).
-template <int BN, int CG = 1> struct UmmaCfg {
+// BK = fp16 elements per k-block: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B: half-size stages, so
+// a 128 x 256 tile gets a FOUR-deep ring in the same shared memory its 64-wide k-blocks only allow two stages of).
+template <int BN, int CG = 1, int BK = UM_BK> struct UmmaCfg {
     static constexpr int B_ROWS = BN / CG;                      // rows of the B tile staged by one CTA
-    static constexpr int STAGES = (B_ROWS == 256) ? 2 : (B_ROWS == 64) ? 4 : 3;
-    static constexpr int A_BYTES = UM_BM * 128;                 // one plane of A per stage
-    static constexpr int B_BYTES = B_ROWS * 128;
+    static constexpr int STAGES = (BK == 32) ? 4 : (B_ROWS == 256) ? 2 : (B_ROWS == 64) ? 4 : 3;
+    static constexpr int A_BYTES = UM_BM * BK * 2;              // one plane of A per stage
+    static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
-    static constexpr int TMEM_COLS = 2 * BN;                    // double-buffered accumulator
+    static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;   // double-buffered accumulator (power of two)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * 4096 /*epilogue staging*/ + 1024 /*align slack*/ +
                                       192 /*barriers, seed slot*/ + 1024 /*LN row stats*/;
 };
@@ -196,6 +198,12 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// the same for 64-byte rows (BK = 32): SWIZZLE_64B (layout type 4), 8-row groups 512 bytes apart
+template <int BK> __device__ __forceinline__ uint64_t umma_smem_desc_bk(uint32_t saddr) {
+    if constexpr (BK == 64) return umma_smem_desc(saddr);
+    else return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+                ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
 // kind::f16 instruction descriptor: D fp32 (bits 4-5 = 1), A/B FP16 (format 0 at bits 7-9 / 10-12),
 // both K-major, N>>3 at bit 17, M>>4 at bit 24.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
@@ -248,7 +256,7 @@ constexpr int UM_THREADS = 64 + 32 * UM_EPI_WARPS;
 
 // DROP (LayerNorm variant only): dropout1 / dropout2 compiled in.  The LayerNorm epilogue is issue-bound, so the
 // deterministic kernel carries none of the mask arithmetic (the non-LN kernels take a warp-uniform branch instead).
-template <int BN, bool LN, bool OUT_HALF, int CG = 1, bool DROP = false>
+template <int BN, bool LN, bool OUT_HALF, int CG = 1, bool DROP = false, int BK = UM_BK>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                  const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
@@ -256,8 +264,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                  const __grid_constant__ CUtensorMap mapR_hi, const __grid_constant__ CUtensorMap mapR_lo,
                  int M, int N, int K, int m_tile0, int m_tile_cnt, Epi ep) {
     const bool pdl_early = ep.pdl_early != 0;
-    using Cfg = UmmaCfg<BN, CG>;
+    using Cfg = UmmaCfg<BN, CG, BK>;
     constexpr int STAGES = Cfg::STAGES;
+    static_assert(BK == 64 || (BK == 32 && !LN && CG == 1), "64-byte k-blocks: plain single-CTA tiles only");
     static_assert(CG == 1 || (CG == 2 && !LN && (BN == 256 || BN == 128)), "pair tiles: 256 x 256 or 256 x 128, no LayerNorm epilogue");
     // 128B-swizzled operand tiles need 1024-byte alignment.  The kernel has no static shared memory,
     // so the dynamic window starts at shared offset 0; keeping the pointer un-cast preserves the
@@ -282,7 +291,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (N + BN - 1) / BN;
     const int total_tiles = n_tiles * (m_tile_cnt / CG);       // m-tiles [m_tile0, m_tile0 + m_tile_cnt), CG per tile
-    const int num_kb = K / UM_BK;
+    const int num_kb = K / BK;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;   // rank 0 = leader: issues the pair's MMAs
     const int grp = blockIdx.x / CG, n_grp = gridDim.x / CG;   // persistent loop over tiles, one CTA group per tile
 
@@ -325,16 +334,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                         // both CTAs' bytes are counted on the LEADER's full barrier (it expects 2 stages' worth)
                         const uint32_t fb = map_to_cta(ptx::smem_u32(&full_bar[stage]), 0u);
                         if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                        ptx::tma_load_2d_pair(s, &mapA_hi, fb, kb * UM_BK, m0);
-                        ptx::tma_load_2d_pair(s + Cfg::A_BYTES, &mapA_lo, fb, kb * UM_BK, m0);
-                        ptx::tma_load_2d_pair(s + 2 * Cfg::A_BYTES, &mapB_hi, fb, kb * UM_BK, n0);
-                        ptx::tma_load_2d_pair(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, fb, kb * UM_BK, n0);
+                        ptx::tma_load_2d_pair(s, &mapA_hi, fb, kb * BK, m0);
+                        ptx::tma_load_2d_pair(s + Cfg::A_BYTES, &mapA_lo, fb, kb * BK, m0);
+                        ptx::tma_load_2d_pair(s + 2 * Cfg::A_BYTES, &mapB_hi, fb, kb * BK, n0);
+                        ptx::tma_load_2d_pair(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, fb, kb * BK, n0);
                     } else {
                         ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                        ptx::tma_load_2d(s, &mapA_hi, &full_bar[stage], kb * UM_BK, m0);
-                        ptx::tma_load_2d(s + Cfg::A_BYTES, &mapA_lo, &full_bar[stage], kb * UM_BK, m0);
-                        ptx::tma_load_2d(s + 2 * Cfg::A_BYTES, &mapB_hi, &full_bar[stage], kb * UM_BK, n0);
-                        ptx::tma_load_2d(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, &full_bar[stage], kb * UM_BK, n0);
+                        ptx::tma_load_2d(s, &mapA_hi, &full_bar[stage], kb * BK, m0);
+                        ptx::tma_load_2d(s + Cfg::A_BYTES, &mapA_lo, &full_bar[stage], kb * BK, m0);
+                        ptx::tma_load_2d(s + 2 * Cfg::A_BYTES, &mapB_hi, &full_bar[stage], kb * BK, n0);
+                        ptx::tma_load_2d(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB_lo, &full_bar[stage], kb * BK, n0);
                     }
                     if (++stage == STAGES) stage = 0;
                 }
@@ -371,11 +380,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                     if (kb == 0 && it == 0) TIP_TS(1);
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint64_t a_hi = umma_smem_desc(sa), a_lo = umma_smem_desc(sa + Cfg::A_BYTES);
-                    const uint64_t b_hi = umma_smem_desc(sa + 2 * Cfg::A_BYTES);
-                    const uint64_t b_lo = umma_smem_desc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                    const uint64_t a_hi = umma_smem_desc_bk<BK>(sa), a_lo = umma_smem_desc_bk<BK>(sa + Cfg::A_BYTES);
+                    const uint64_t b_hi = umma_smem_desc_bk<BK>(sa + 2 * Cfg::A_BYTES);
+                    const uint64_t b_lo = umma_smem_desc_bk<BK>(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < UM_BK / 16; ++k) {
+                    for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 16 fp16 = 32 bytes along K
                         if constexpr (CG == 2) {
                             ptx::umma_f16_pair(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
@@ -439,10 +448,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                     const float sc = asc * osc;
                     uint8_t* sbuf = reinterpret_cast<uint8_t*>(stg);
                     const float* bs = row_stat + (it & 1) * 256 + half * (BN / 2);
+                    // the next chunk's accumulator columns are requested from tensor memory before this chunk is processed
+                    // (tcgen05.ld latency under the bias / split / store work instead of in front of it)
+                    ptx::tmem_ld32(t_acc, v);
 #pragma unroll 1
                     for (int c = 0; c < CH; ++c) {
                         const int colb = n0 + half * (BN / 2) + c * 32;
-                        ptx::tmem_ld32(t_acc + c * 32, v);
+                        float vn[32];
+                        if (c + 1 < CH) ptx::tmem_ld32_nowait(t_acc + (c + 1) * 32, vn);
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
                             const float4 b = *reinterpret_cast<const float4*>(bs + c * 32 + 4 * j4);       // broadcast
@@ -517,6 +530,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                                 ptx::tma_store_2d(&mapC0, sbuf, colb, rbase);
                                 ptx::bulk_commit();
                             }
+                        }
+                        if (c + 1 < CH) {
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = vn[j];
                         }
                     }
                 } else if (fast) {
@@ -776,6 +794,8 @@ struct UmmaMaps {
     UmmaOperand w_qkv256[MAX_LAYERS], w_1256[MAX_LAYERS], w_ih256;        // 256-row boxes of the same planes (wide tiles)
     UmmaOperand w_o64[MAX_LAYERS], w_264[MAX_LAYERS];                     // 64-row boxes (skinny-M LayerNorm GEMMs, 4 CTAs per row tile)
     UmmaOperand w_qkv64[MAX_LAYERS], w_164[MAX_LAYERS], w_ih64;           // 64-row boxes: each CTA of a 256 x 128 pair tile stages half of B
+    UmmaOperand a_xa32, a_xb32, w_qkv256k32[MAX_LAYERS], w_1256k32[MAX_LAYERS];   // 32-column (64-byte, SWIZZLE_64B) k-blocks: 128 x 256 tiles with a 4-stage ring
+    UmmaOperand a_xin32, a_hs32, w_in256k32, w_l192k32;                            // ... in_linear as ONE 128 x 256 tile per row tile, the head as ONE 128 x 192 tile
     UmmaOutput o_pre;                                                      // fp32 [rows][256] scratch of the un-fused LayerNorm path
     UmmaOutput o_xa, o_xb, o_hid, o_qkv, o_gi;                             // TMA-store targets
     UmmaOperand w_hh;                                                      // resident A operand of the recurrence (box 64 x 64)
@@ -801,15 +821,15 @@ inline tip_encode_tiled_fn umma_encode_fn() {
 }
 
 // 2-D fp16 row-major [rows][cols] plane, box = 64 columns (128 bytes, swizzled) x box_rows rows
-inline bool umma_make_map(CUtensorMap* map, const __half* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+inline bool umma_make_map(CUtensorMap* map, const __half* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bk = UM_BK) {
     tip_encode_tiled_fn enc = umma_encode_fn();
     if (!enc) return false;
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {cols * sizeof(__half)};
-    cuuint32_t box[2] = {(cuuint32_t)UM_BK, box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, box_rows};
     cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), gdim, gstride, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -849,17 +869,23 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
     outp(mp.o_gi, gi, 0, R, false);
     outp(mp.o_pre, pre, 0, E, false);        // fp32 [rows][256] scratch of the un-fused LayerNorm path
     // activation planes: hi at the start of the buffer, lo `plane` halves later (same bytes as one fp32 plane)
-    auto act = [&](UmmaOperand& op, const float* p, size_t plane, int cols) {
+    auto act = [&](UmmaOperand& op, const float* p, size_t plane, int cols, int bk = UM_BK) {
         const __half* h = reinterpret_cast<const __half*>(p);
-        ok = ok && umma_make_map(&op.hi, h, cap_rows, cols, UM_BM) && umma_make_map(&op.lo, h + plane, cap_rows, cols, UM_BM);
+        ok = ok && umma_make_map(&op.hi, h, cap_rows, cols, UM_BM, bk) && umma_make_map(&op.lo, h + plane, cap_rows, cols, UM_BM, bk);
     };
-    auto wgt = [&](UmmaOperand& op, size_t hi, size_t lo, int rows, int cols, int bn) {
-        ok = ok && umma_make_map(&op.hi, reinterpret_cast<const __half*>(blob + hi), rows, cols, bn) &&
-             umma_make_map(&op.lo, reinterpret_cast<const __half*>(blob + lo), rows, cols, bn);
+    auto wgt = [&](UmmaOperand& op, size_t hi, size_t lo, int rows, int cols, int bn, int bk = UM_BK) {
+        ok = ok && umma_make_map(&op.hi, reinterpret_cast<const __half*>(blob + hi), rows, cols, bn, bk) &&
+             umma_make_map(&op.lo, reinterpret_cast<const __half*>(blob + lo), rows, cols, bn, bk);
     };
     act(mp.a_xin, xin, plane_xin, d.kin_pad);
     act(mp.a_xa, xa, plane_e, E);
     act(mp.a_xb, xb, plane_e, E);
+    act(mp.a_xa32, xa, plane_e, E, 32);
+    act(mp.a_xin32, xin, plane_xin, d.kin_pad, 32);
+    act(mp.a_hs32, hs, plane_r, R, 32);
+    wgt(mp.w_in256k32, o.win_hi, o.win_lo, E, d.kin_pad, 256, 32);
+    wgt(mp.w_l192k32, o.wl_hi, o.wl_lo, HEAD_NPAD, d.khead, 192, 32);      // rows 144..191 of the box: out of bounds -> zero fill
+    act(mp.a_xb32, xb, plane_e, E, 32);
     act(mp.a_att, att, plane_e, E);
     act(mp.a_hid, hid, plane_f, F);
     act(mp.a_hs, hs, plane_r, R);
@@ -874,6 +900,8 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         wgt(mp.w_264[l], L.w2_hi, L.w2_lo, E, F, 64);
         wgt(mp.w_1256[l], L.w1_hi, L.w1_lo, F, E, 256);
         wgt(mp.w_qkv64[l], L.wqkv_hi, L.wqkv_lo, 3 * E, E, 64);
+        wgt(mp.w_qkv256k32[l], L.wqkv_hi, L.wqkv_lo, 3 * E, E, 256, 32);
+        wgt(mp.w_1256k32[l], L.w1_hi, L.w1_lo, F, E, 256, 32);
         wgt(mp.w_164[l], L.w1_hi, L.w1_lo, F, E, 64);
         wgt(mp.w_2[l], L.w2_hi, L.w2_lo, E, F, 256);
     }
@@ -896,6 +924,8 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         cudaFuncSetAttribute(umma_gemm_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256, 2>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<256, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256, 2>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<256, false, true, 1, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256, 1, 32>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<192, false, false, 1, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<192, 1, 32>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<128, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 2>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<128, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 2>::SMEM_BYTES);
         mp.attrs_set = true;
@@ -903,8 +933,14 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
     return TIP_OK;
 }
 
-inline bool wide_mode() {      // experiment: 128 x 256 single-CTA tiles (measured: no gain, the 2-stage ring exposes latency)
+inline int wide_kind() {       // TIP_BN256: 1 = 128 x 256 single-CTA tiles, 64-wide k-blocks (2-stage ring: exposes TMA latency, measured no gain);
+                               //            2 = the same tiles with 32-wide k-blocks (4-stage ring), qkv and ff1 only
     static const int v = getenv("TIP_BN256") ? atoi(getenv("TIP_BN256")) : 0;
+    return v;
+}
+inline bool wide_mode() { return wide_kind() == 1; }
+inline bool one_tile_mode() {  // TIP_ONE_TILE=1: in_linear (N = 256) and the head (N <= 144) as ONE tile per 128-row tile (A read once; 32-wide k-blocks)
+    static const int v = getenv("TIP_ONE_TILE") ? atoi(getenv("TIP_ONE_TILE")) : 0;
     return v != 0;
 }
 inline int pair_kind() {       // TIP_PAIR: 1 = 256 x 256 pair tiles, 2 = 256 x 128 pair tiles (each CTA: its 128 rows of A, 64 rows of B)
@@ -990,6 +1026,16 @@ inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, c
             cudaLaunchKernelEx(&cfg, umma_gemm_kernel<256, false, true, 2>, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
         else
             cudaLaunchKernelEx(&cfg, umma_gemm_kernel<256, false, false, 2>, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+    } else if ((which == UG_HEAD_R || which == UG_HEAD_E) && one_tile_mode() && m_tiles >= 64) {
+        const UmmaOperand* A32 = (which == UG_HEAD_R) ? &mp.a_hs32 : &mp.a_xa32;
+        launch_k(umma_gemm_kernel<192, false, false, 1, false, 32>, dim3(std::min(m_tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<192, 1, 32>::SMEM_BYTES, st, A32->hi, A32->lo, mp.w_l192k32.hi, mp.w_l192k32.lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+    } else if (which == UG_IN && ep.out_lo && one_tile_mode() && m_tiles >= 64) {
+        launch_k(umma_gemm_kernel<256, false, true, 1, false, 32>, dim3(std::min(m_tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<256, 1, 32>::SMEM_BYTES, st, mp.a_xin32.hi, mp.a_xin32.lo, mp.w_in256k32.hi, mp.w_in256k32.lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+    } else if ((which == UG_QKV || which == UG_FF1) && ep.out_lo && m_tiles * (N / 256) >= mp.num_sms && wide_kind() == 2) {
+        const UmmaOperand* A32 = (which == UG_QKV) ? &mp.a_xa32 : &mp.a_xb32;
+        const UmmaOperand* B32 = (which == UG_QKV) ? &mp.w_qkv256k32[layer] : &mp.w_1256k32[layer];
+        const int tiles = m_tiles * (N / 256);
+        launch_k(umma_gemm_kernel<256, false, true, 1, false, 32>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<256, 1, 32>::SMEM_BYTES, st, A32->hi, A32->lo, B32->hi, B32->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
     } else if (B256 && (N % 256) == 0 && m_tiles * (N / 256) >= mp.num_sms && wide_mode()) {
         // wide tiles: A is re-used over 256 columns (25 % less L2->SM operand traffic per flop)
         const int tiles = m_tiles * (N / 256);
