@@ -10,6 +10,7 @@
 #include "tip_umma.cuh"
 #include "tip_rnn_umma.cuh"
 #include "tip_attn_mma.cuh"
+#include "tip_qkv_attn.cuh"
 
 using namespace tip;
 
@@ -79,7 +80,7 @@ struct tip_model {
     int64_t last_rows = 0;
     int rnn_clusters = -1;          // co-schedulable 8-CTA clusters (queried on first use)
     int rnn_umma_clusters = -1;
-    bool attn_attr_set = false;
+    bool attn_attr_set = false, qa_attr_set = false;
     int rnn_stream_fallback = 0;    // TIP_RNN_STREAM=1: L2-streaming kernel (debug / comparison)
     std::string err;
 
@@ -188,6 +189,7 @@ static void compute_offsets(tip_model* m) {
         L.wo_hi = take((size_t)E * E);       L.wo_lo = take((size_t)E * E);
         L.w1_hi = take((size_t)F * E);       L.w1_lo = take((size_t)F * E);
         L.w2_hi = take((size_t)E * F);       L.w2_lo = take((size_t)E * F);
+        L.wqkvr_hi = take((size_t)3 * E * E / 2); L.wqkvr_lo = take((size_t)3 * E * E / 2); L.bqkvr = take(3 * E);
     }
     if (d.with_rnn) {
         o.wih = take((size_t)R * E); o.brnn = take(R);
@@ -418,6 +420,10 @@ extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64
         split(L.wo, L.wo_hi, L.wo_lo, (size_t)E * E, SC_LAYER0 + 4 * l + 1, ACT_SCALE);
         split(L.w1, L.w1_hi, L.w1_lo, (size_t)F * E, SC_LAYER0 + 4 * l + 2, ACT_SCALE);
         split(L.w2, L.w2_hi, L.w2_lo, (size_t)E * F, SC_LAYER0 + 4 * l + 3, ACT_SCALE);
+        // the same in_proj planes with their rows grouped per 4 heads (q | k | v of the group contiguous): fused QKV + attention
+        pack_qkv_reorder_kernel<<<(3 * E * (E / 8) + 255) / 256, 256, 0, st>>>(
+            reinterpret_cast<const __half*>(B + L.wqkv_hi), reinterpret_cast<const __half*>(B + L.wqkv_lo), B + L.bqkv,
+            reinterpret_cast<__half*>(B + L.wqkvr_hi), reinterpret_cast<__half*>(B + L.wqkvr_lo), B + L.bqkvr);
         i += 12;
     }
     if (d.with_rnn) {
@@ -588,6 +594,33 @@ static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, fl
     if (B >= 32 && akind == 1) attention_kernel<4, 4><<<dim3(B, NH / 4), 320, 0, st>>>(qkv, out, out_lo, L, drop_p, sp, seed, b0);
     else if (B >= 32) attention_kernel<2, 4><<<dim3(B, NH / 4), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, sp, seed, b0);
     else         attention_kernel<4, 2><<<dim3(B, NH / 2), 160, 0, st>>>(qkv, out, out_lo, L, drop_p, sp, seed, b0);
+    m->launches++;
+}
+
+// fused QKV projection + attention of layer l for the windows [w0, w0 + nw): xa -> att (FP16 hi/lo planes)
+// TIP_FUSED_ATTN: 0 never, 1 always, 2 (default) when the forward's work units fit ONE wave (<= 148 units = 111 windows at
+// L = 40).  Measured (stage times incl. ~4 us of event overhead per kernel): B = 1: 20.4 vs 11.0 + 10.4 us for the QKV GEMM +
+// attention kernels, B = 64: 21.0 vs 24.4, B = 256: 44.9 vs 22.5 + 18.4 -- with several rounds per SM the attention
+// epilogue (CUDA cores, 8 warps per SM: 49 % issue utilisation, ncu) is slower than the dedicated one-wave mma.sync kernel.
+static int fused_attn_kind() {
+    static const int v = getenv("TIP_FUSED_ATTN") ? atoi(getenv("TIP_FUSED_ATTN")) : 2;
+    return v;
+}
+static void launch_qkv_attn(tip_model* m, cudaStream_t st, int l, int w0, int nw, int L, float drop_p, uint64_t seed_off, int pdl_early) {
+    pdl_kind() = 1;
+    if (!m->qa_attr_set) {
+        cudaFuncSetAttribute(qkv_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES);
+        m->qa_attr_set = true;
+    }
+    const LayerOff& Lo = m->off.layer[l];
+    const int wpt = UM_BM / L;
+    const int units = ((nw + wpt - 1) / wpt) * QA_GROUPS;
+    __half* oh = reinterpret_cast<__half*>(m->att);
+    __half* ol = reinterpret_cast<__half*>(m->att + m->plane_e / 2);
+    launch_k(qkv_attn_kernel, dim3(std::min(units, m->maps.num_sms)), dim3(UM_THREADS), QA_SMEM_BYTES, st,
+             m->maps.a_xa32.hi, m->maps.a_xa32.lo, m->maps.w_qkvr[l].hi, m->maps.w_qkvr[l].lo,
+             (const float*)(m->blob + Lo.bqkvr), oh, ol, (const float*)(m->blob + m->off.scales + SC_LAYER0 + 4 * l + 0),
+             w0, nw, L, drop_p, drop_threshold(drop_p), (const uint64_t*)m->d_seed, seed_off, pdl_early);
     m->launches++;
 }
 
@@ -808,12 +841,20 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
     gemm(UG_IN, 0, m->xin, d.kin_pad, W + o.win, E, ep, false);
     for (int l = 0; l < d.layers; ++l) {                                        // reference :91
         const LayerOff& Lo = o.layer[l];
+        const int qa_units = ((nw + UM_BM / L - 1) / (UM_BM / L)) * QA_GROUPS;
+        const bool fused = umma && (L % 2) == 0 &&                 // (the fused kernel pairs adjacent queries of a window: even L)
+                           (fused_attn_kind() == 1 || (fused_attn_kind() == 2 && qa_units <= 148));
+        if (fused) {
+            mark(m, st, "qkv_attn", l);             // projection + attention in one kernel: q | k | v never leave the SM
+            launch_qkv_attn(m, st, l, w0, nw, L, p_enc, seed + seed_attn(l), (M - R0 <= 1024) ? 1 : 0);
+        } else {
         mark(m, st, "qkv", l);
         ep = Epi{}; ep.bias = W + Lo.bqkv; ep.out = m->qkv; ep.ldc = 3 * E;
         if (umma) ep.out_lo = m->qkv + (size_t)m->cap_rows * 3 * E / 2;     // FP16 planes for the mma attention
         gemm(UG_QKV, l, m->xa, E, W + Lo.wqkv, 3 * E, ep, false);
         mark(m, st, "attention", l);
         launch_attention(m, st, m->qkv, m->att, lo_att, nw, L, p_enc, seed + seed_attn(l), R0);
+        }
         mark(m, st, "out_proj_ln", l);
         ep = Epi{}; ep.bias = W + Lo.bo; ep.resid = m->xa; ep.resid_lo = lo_xa; ep.ldr = E;
         ep.gamma = W + Lo.g1; ep.beta = W + Lo.be1; ep.out = m->xb; ep.out_lo = lo_xb; ep.ldc = E;

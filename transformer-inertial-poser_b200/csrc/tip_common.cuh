@@ -29,6 +29,7 @@ constexpr int HEAD_NPAD = 144;  // size_s (<=144) padded to a legal UMMA N (mult
 struct LayerOff {
     size_t wqkv, bqkv, wo, bo, w1, b1, w2, b2, g1, be1, g2, be2;
     size_t wqkv_hi, wqkv_lo, wo_hi, wo_lo, w1_hi, w1_lo, w2_hi, w2_lo;
+    size_t wqkvr_hi, wqkvr_lo, bqkvr;      // in_proj rows / bias re-ordered per head group (fused QKV + attention kernel)
 };
 // index of a matrix in the `scales` table
 constexpr int SC_IN = 0, SC_LAYER0 = 1 /* + 4*layer + {qkv,o,1,2} */, SC_IH = 1 + 4 * MAX_LAYERS, SC_HEAD = SC_IH + 1,

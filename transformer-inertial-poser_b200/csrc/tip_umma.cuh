@@ -795,6 +795,7 @@ struct UmmaMaps {
     UmmaOperand w_o64[MAX_LAYERS], w_264[MAX_LAYERS];                     // 64-row boxes (skinny-M LayerNorm GEMMs, 4 CTAs per row tile)
     UmmaOperand w_qkv64[MAX_LAYERS], w_164[MAX_LAYERS], w_ih64;           // 64-row boxes: each CTA of a 256 x 128 pair tile stages half of B
     UmmaOperand a_xa32, a_xb32, w_qkv256k32[MAX_LAYERS], w_1256k32[MAX_LAYERS];   // 32-column (64-byte, SWIZZLE_64B) k-blocks: 128 x 256 tiles with a 4-stage ring
+    UmmaOperand w_qkvr[MAX_LAYERS];                                                // re-ordered in_proj rows, 192-row x 32-column boxes (fused QKV + attention)
     UmmaOperand a_xin32, a_hs32, w_in256k32, w_l192k32;                            // ... in_linear as ONE 128 x 256 tile per row tile, the head as ONE 128 x 192 tile
     UmmaOutput o_pre;                                                      // fp32 [rows][256] scratch of the un-fused LayerNorm path
     UmmaOutput o_xa, o_xb, o_hid, o_qkv, o_gi;                             // TMA-store targets
@@ -901,6 +902,7 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         wgt(mp.w_1256[l], L.w1_hi, L.w1_lo, F, E, 256);
         wgt(mp.w_qkv64[l], L.wqkv_hi, L.wqkv_lo, 3 * E, E, 64);
         wgt(mp.w_qkv256k32[l], L.wqkv_hi, L.wqkv_lo, 3 * E, E, 256, 32);
+        wgt(mp.w_qkvr[l], L.wqkvr_hi, L.wqkvr_lo, 3 * E, E, 192, 32);
         wgt(mp.w_1256k32[l], L.w1_hi, L.w1_lo, F, E, 256, 32);
         wgt(mp.w_164[l], L.w1_hi, L.w1_lo, F, E, 64);
         wgt(mp.w_2[l], L.w2_hi, L.w2_lo, E, F, 256);
