@@ -521,15 +521,28 @@ def test_raw_imu_preprocessing_on_device():
 def test_batch_sizes_across_kernel_switch_points(engine):
     """L = 40 at batch sizes on both sides of every dispatch threshold: skinny LayerNorm path (<= 8 row tiles,
     B <= 25), small-batch recurrence with 1 / 2 / 4 / 8 windows per cluster, FFMA cluster recurrence, tensor-core
-    recurrence (> ~120 windows), programmatic dependent launch (<= 1024 rows)."""
+    recurrence (> ~120 windows), programmatic dependent launch (<= 1024 rows), fused QKV + attention kernel
+    (<= 148 work units = 111 windows; ragged last row tile at B % 3 != 0)."""
     sd = O.random_state_dict(23)
     m = make_model(sd, engine=engine)
-    for seed, B in enumerate([1, 2, 9, 16, 17, 25, 26, 31, 61, 100, 121, 140]):
+    for seed, B in enumerate([1, 2, 9, 16, 17, 25, 26, 31, 61, 100, 110, 111, 112, 121, 140]):
         x_imu, x_s = O.synth_inputs(300 + seed, B, 40, nan_frac=0.1)
         y = run(m, x_imu, x_s)
         ref = O.forward(sd, x_imu, x_s)
         err = np.abs(y - ref).max()
         assert np.isfinite(y).all() and err < TOL, (B, err)
+
+
+@pytest.mark.parametrize("L", [2, 8, 22, 38, 39, 40])
+def test_fused_qkv_attention_window_lengths(L):
+    """The fused QKV + attention kernel cuts its 128-row tiles on window boundaries (128 // L windows per tile) and pairs
+    adjacent queries (even L); odd L and large batches take the two-kernel path.  Same answers either way."""
+    sd = O.random_state_dict(41)
+    m = make_model(sd)
+    for B in (1, 5, 37):
+        x_imu, x_s = O.synth_inputs(500 + L + B, B, L)
+        y = run(m, x_imu, x_s)
+        assert np.abs(y - O.forward(sd, x_imu, x_s)).max() < TOL, (L, B)
 
 
 def test_head_variants_at_batch_sizes():
