@@ -107,3 +107,34 @@ def test_unmodified_offline_testing_simple_through_the_dropin(tmp_path):
     # stochastic on both sides (different generators): same accuracy band
     assert abs(ours_s["metrics"]["joint_angle_err_deg"] - ref_s["metrics"]["joint_angle_err_deg"]) < 0.25 * ref_s["metrics"]["joint_angle_err_deg"]
     assert abs(ours_s["metrics"]["joint_pos_err_cm"] - ref_s["metrics"]["joint_pos_err_cm"]) < 0.25 * ref_s["metrics"]["joint_pos_err_cm"]
+
+
+def test_long_closed_loop_600_frames_no_drift(tmp_path):
+    """Closed loop far beyond one window (600 frames = 10 s at 60 Hz, the script's --test_len): the drop-in and the
+    reference model (torch eager, same GPU) drive the unmodified RTRunnerMin on the same synthetic motion; the fed-back
+    state must not drift apart (the loop is contractive: the root rotation comes from the IMU every frame)."""
+    import pickle
+    wd = str(tmp_path)
+    with CE.consumer_env(dropin=False, workdir=wd):
+        path = CE.write_synthetic_dip(wd, n_motions=1, T=600, seed=21)[0]
+    motion = pickle.load(open(path, "rb"))
+
+    def run(dropin):
+        with CE.consumer_env(dropin=dropin, deterministic=True, workdir=wd) as stws:
+            from real_time_runner_minimal import RTRunnerMin
+            m = CE.build_model(stws)
+            r = RTRunnerMin(CE.make_char(), m, 40, motion["nimble_qdq"][0], with_acc_sum=True)
+            prev = motion["nimble_qdq"][0][:3].copy()
+            out = []
+            for t in range(600):
+                with torch.no_grad():
+                    res = r.step(motion["imu"][t], prev)
+                prev = res["qdq"][:3].copy()
+                out.append(np.concatenate((res["qdq"], res["ct"])))
+            return np.array(out)
+    a, b = run(True), run(False)
+    err = np.abs(a[:, 3:60] - b[:, 3:60]).max(axis=1)
+    assert err.max() < 2e-3, (err.max(), int(err.argmax()))
+    assert err[400:].max() < 2 * max(err[:200].max(), 2e-4)                 # no growth over the run
+    flips = int((a[:, 114::4] != b[:, 114::4]).sum())
+    assert flips <= 2, flips                                                # contact flags (thresholded logits)
