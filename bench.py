@@ -800,11 +800,12 @@ def main():
     stage_flops = {"in_linear": 2.0 * M * 221 * 256, "qkv": 2.0 * M * 256 * 768,
                    "attention": 2.0 * B * 2 * L_WIN * L_WIN * 256, "out_proj_ln": 2.0 * M * 256 * 256,
                    "qkv_attn": 2.0 * M * 256 * 768 + 2.0 * B * 2 * L_WIN * L_WIN * 256,
+                   "ffn_ln": 2.0 * M * 256 * 1024 + 2.0 * M * 1024 * 256,
                    "ff1": 2.0 * M * 256 * 1024, "ff2_ln": 2.0 * M * 1024 * 256,
                    "rnn_ih": 2.0 * M * 256 * 512, "rnn": 2.0 * M * 512 * 512, "head": 2.0 * M * 512 * 131,
                    "condition": 0.0}
     per_launch = {k: float(np.mean(v)) for k, v in stage_ms.items()}
-    launches_per_fwd = {k: (4 if k in ("qkv", "attention", "qkv_attn", "out_proj_ln", "ff1", "ff2_ln") else 1) for k in per_launch}
+    launches_per_fwd = {k: (4 if k in ("qkv", "attention", "qkv_attn", "out_proj_ln", "ff1", "ff2_ln", "ffn_ln") else 1) for k in per_launch}
     totals = {k: per_launch[k] * launches_per_fwd[k] for k in per_launch}
     dom = max(totals, key=totals.get)
     tot_stage = sum(totals.values())

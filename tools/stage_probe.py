@@ -19,5 +19,5 @@ for B in [int(b) for b in os.environ.get('BS','1,8,16,64,128,256,512').split(','
         m(xi, xs); 
         for n, l, ms in m.profile(): acc.setdefault(n, []).append(ms)
     d={k: round(float(np.mean(v))*1e3,1) for k, v in acc.items()}
-    tot=sum(v*(4 if k in ('qkv','attention','qkv_attn','out_proj_ln','ff1','ff2_ln') else 1) for k,v in d.items())
+    tot=sum(v*(4 if k in ('qkv','attention','qkv_attn','out_proj_ln','ff1','ff2_ln','ffn_ln') else 1) for k,v in d.items())
     print(B, round(tot,1), d)

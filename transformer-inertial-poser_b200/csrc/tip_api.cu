@@ -11,6 +11,7 @@
 #include "tip_rnn_umma.cuh"
 #include "tip_attn_mma.cuh"
 #include "tip_qkv_attn.cuh"
+#include "tip_ffn_fused.cuh"
 
 using namespace tip;
 
@@ -80,7 +81,7 @@ struct tip_model {
     int64_t last_rows = 0;
     int rnn_clusters = -1;          // co-schedulable 8-CTA clusters (queried on first use)
     int rnn_umma_clusters = -1;
-    bool attn_attr_set = false, qa_attr_set = false;
+    bool attn_attr_set = false, qa_attr_set = false, ffn_attr_set = false;
     int rnn_stream_fallback = 0;    // TIP_RNN_STREAM=1: L2-streaming kernel (debug / comparison)
     std::string err;
 
@@ -624,6 +625,47 @@ static void launch_qkv_attn(tip_model* m, cudaStream_t st, int l, int w0, int nw
     m->launches++;
 }
 
+// fused feed-forward block of layer l (ff1 + ReLU [+ dropout] + ff2 [+ dropout2] + residual + LayerNorm2) for the row tiles
+// [T0, T0 + TN): xb -> xa; the hidden activation stays on the SM.  TIP_FFN_FUSED: 0 (default) never, 1 always, 2: when the
+// forward has more row tiles than the un-fused LayerNorm path takes (TIP_SKINNY_TILES, 74).  Parity-green (it runs the
+// B = 256 goldens and the mask-for-mask stochastic tests when switched on) but not faster: 63.3 us per layer at B = 256
+// against 25.7 + 30.6 us for ff1 and ff2 + LayerNorm, 3 lanes 415 vs 411 us per forward.  ncu: the tensor pipe of the 80 busy
+// SMs is 88 % active yet delivers 44 % of its peak -- the kernel is SHARED-MEMORY-BANDWIDTH bound: every k-step of a
+// 128 x N tile reads 3 x (128 + N) x 32 B of operands (three MMAs of the split), i.e. 128 B/clk at N = 128, all the SM has,
+// while TMA writes the next stages and the epilogue writes hidA into the same memory.  (The same arithmetic explains the
+// 40-45 % tensor-pipe ceiling of the 128 x 128 GEMMs.)
+static int ffn_fused_kind() {
+    static const int v = getenv("TIP_FFN_FUSED") ? atoi(getenv("TIP_FFN_FUSED")) : 0;
+    return v;
+}
+static void launch_ffn(tip_model* m, cudaStream_t st, int l, int M, int T0, int TN, float drop_p, uint64_t seed_base, int pdl_early) {
+    pdl_kind() = 1;
+    if (!m->ffn_attr_set) {
+        cudaFuncSetAttribute(ffn_ln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES);
+        cudaFuncSetAttribute(ffn_ln_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES);
+        m->ffn_attr_set = true;
+    }
+    const LayerOff& Lo = m->off.layer[l];
+    const float* W = m->blob;
+    FfnArgs a{};
+    a.b1 = W + Lo.b1; a.b2 = W + Lo.b2; a.gamma = W + Lo.g2; a.beta = W + Lo.be2;
+    a.sc1 = W + m->off.scales + SC_LAYER0 + 4 * l + 2;
+    a.sc2 = W + m->off.scales + SC_LAYER0 + 4 * l + 3;
+    a.M = M; a.m_tile0 = T0; a.m_tiles = TN;
+    a.drop_thr = drop_threshold(drop_p); a.drop_inv = drop_inv_keep(drop_p);
+    a.seed_ptr = m->d_seed; a.seed_ff1 = seed_base + seed_ff1(l); a.seed_ff2 = seed_base + seed_ff2(l);
+    a.pdl_early = pdl_early;
+    const UmmaMaps& mp = m->maps;
+    const dim3 grid(std::min(TN, mp.num_sms));
+    if (a.drop_thr)
+        launch_k(ffn_ln_kernel<true>, grid, dim3(UM_THREADS), FF_SMEM_BYTES, st, mp.a_xb32.hi, mp.a_xb32.lo, mp.w_1k32[l].hi, mp.w_1k32[l].lo,
+                 mp.w_2k32[l].hi, mp.w_2k32[l].lo, mp.a_xb.hi, mp.a_xb.lo, mp.o_xa.c0, mp.o_xa.c1, a);
+    else
+        launch_k(ffn_ln_kernel<false>, grid, dim3(UM_THREADS), FF_SMEM_BYTES, st, mp.a_xb32.hi, mp.a_xb32.lo, mp.w_1k32[l].hi, mp.w_1k32[l].lo,
+                 mp.w_2k32[l].hi, mp.w_2k32[l].lo, mp.a_xb.hi, mp.a_xb.lo, mp.o_xa.c0, mp.o_xa.c1, a);
+    m->launches++;
+}
+
 static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs, float* hs_lo, int B, int L) {
     pdl_kind() = 4;
     if (m->rnn_clusters < 0) {
@@ -860,6 +902,12 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
         ep.gamma = W + Lo.g1; ep.beta = W + Lo.be1; ep.out = m->xb; ep.out_lo = lo_xb; ep.ldc = E;
         ep.drop_p = p_enc; ep.seed = seed + seed_out(l);
         gemm(UG_OUT, l, m->att, E, W + Lo.wo, E, ep, true);
+        static const int skinny_tiles_ffn = getenv("TIP_SKINNY_TILES") ? atoi(getenv("TIP_SKINNY_TILES")) : 74;
+        if (umma && m->maps.o_xa.valid && (ffn_fused_kind() == 1 || (ffn_fused_kind() == 2 && TN > skinny_tiles_ffn))) {
+            mark(m, st, "ffn_ln", l);               // ff1 + ff2 + residual + LayerNorm2 in one kernel: `hid` never leaves the SM
+            launch_ffn(m, st, l, M, T0, TN, p_enc, seed, (M - R0 <= 1024) ? 1 : 0);
+            continue;
+        }
         mark(m, st, "ff1", l);
         ep = Epi{}; ep.bias = W + Lo.b1; ep.relu = 1; ep.out = m->hid; ep.out_lo = lo_hid; ep.ldc = F;
         ep.drop_p = p_enc; ep.seed = seed + seed_ff1(l);

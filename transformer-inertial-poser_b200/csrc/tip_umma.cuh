@@ -432,7 +432,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                 // this tile's bias slice (pre-multiplied by the output scale) -> shared memory while the MMAs still run:
                 // the kernel leaves ~3 KB of L1, so a __ldg in the chunk loop is an exposed L2 round trip
                 const int et = (int)threadIdx.x - 64;
-                if (et < BN) row_stat[(it & 1) * 256 + et] = (n0 + et < N) ? __ldg(ep.bias + n0 + et) * osc : 0.f;
+                // (with dropout on this GEMM's output the kept elements' 1/(1-p) rides on the bias and the accumulator scale)
+                if (et < BN) row_stat[(it & 1) * 256 + et] = (n0 + et < N) ? __ldg(ep.bias + n0 + et) * osc * (ep.drop_thr ? ep.drop_inv : 1.f) : 0.f;
                 if (it == 0 && et == 0) *seed_slot = ep.drop_thr ? site_seed(ep.seed_ptr, ep.seed) : 0ull;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
@@ -445,7 +446,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                 if (ep.tma_out && (n0 + BN <= N) && !(ep.dbg & 7)) {
                     // thread = accumulator row: bias/ReLU/split in registers, 32x32 output box through a
                     // swizzled 4 KB shared tile, written to global by TMA (no transposition, no LSU stores)
-                    const float sc = asc * osc;
+                    const float sc = asc * osc * (ep.drop_thr ? ep.drop_inv : 1.f);
                     uint8_t* sbuf = reinterpret_cast<uint8_t*>(stg);
                     const float* bs = row_stat + (it & 1) * 256 + half * (BN / 2);
                     // the next chunk's accumulator columns are requested from tensor memory before this chunk is processed
@@ -467,10 +468,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                         if (ep.drop_thr) {                            // reference: dropout(relu(linear1(x))) -- warp-uniform branch
                             const uint64_t g0 = ((uint64_t)(rbase + lane) * N + colb) >> 2;
                             const uint64_t dseed = *seed_slot;
+                            const uint32_t thr_hi = ep.drop_thr << 16;
 #pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                const float4 f = dropout_factor4(dseed, g0 + j4, ep.drop_thr, ep.drop_inv);
-                                v[4 * j4 + 0] *= f.x; v[4 * j4 + 1] *= f.y; v[4 * j4 + 2] *= f.z; v[4 * j4 + 3] *= f.w;
+                            for (int j4 = 0; j4 < 8; ++j4) {               // one hash per four columns; a dropped element is one compare + select
+                                const uint64_t h = hash_u64(dseed, g0 + j4);
+                                const uint32_t hl = (uint32_t)h, hh = (uint32_t)(h >> 32);
+                                if ((hl << 16) < thr_hi) v[4 * j4 + 0] = 0.f;
+                                if (hl < thr_hi) v[4 * j4 + 1] = 0.f;
+                                if ((hh << 16) < thr_hi) v[4 * j4 + 2] = 0.f;
+                                if (hh < thr_hi) v[4 * j4 + 3] = 0.f;
                             }
                         }
                         if constexpr (OUT_HALF) {
@@ -795,6 +801,7 @@ struct UmmaMaps {
     UmmaOperand w_o64[MAX_LAYERS], w_264[MAX_LAYERS];                     // 64-row boxes (skinny-M LayerNorm GEMMs, 4 CTAs per row tile)
     UmmaOperand w_qkv64[MAX_LAYERS], w_164[MAX_LAYERS], w_ih64;           // 64-row boxes: each CTA of a 256 x 128 pair tile stages half of B
     UmmaOperand a_xa32, a_xb32, w_qkv256k32[MAX_LAYERS], w_1256k32[MAX_LAYERS];   // 32-column (64-byte, SWIZZLE_64B) k-blocks: 128 x 256 tiles with a 4-stage ring
+    UmmaOperand w_1k32[MAX_LAYERS], w_2k32[MAX_LAYERS];                            // W1 (128-row boxes) / W2 (256-row boxes), 32-column k-blocks: fused FFN kernel
     UmmaOperand w_qkvr[MAX_LAYERS];                                                // re-ordered in_proj rows, 192-row x 32-column boxes (fused QKV + attention)
     UmmaOperand a_xin32, a_hs32, w_in256k32, w_l192k32;                            // ... in_linear as ONE 128 x 256 tile per row tile, the head as ONE 128 x 192 tile
     UmmaOutput o_pre;                                                      // fp32 [rows][256] scratch of the un-fused LayerNorm path
@@ -903,6 +910,8 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         wgt(mp.w_qkv64[l], L.wqkv_hi, L.wqkv_lo, 3 * E, E, 64);
         wgt(mp.w_qkv256k32[l], L.wqkv_hi, L.wqkv_lo, 3 * E, E, 256, 32);
         wgt(mp.w_qkvr[l], L.wqkvr_hi, L.wqkvr_lo, 3 * E, E, 192, 32);
+        wgt(mp.w_1k32[l], L.w1_hi, L.w1_lo, F, E, 128, 32);
+        wgt(mp.w_2k32[l], L.w2_hi, L.w2_lo, E, F, 256, 32);
         wgt(mp.w_1256k32[l], L.w1_hi, L.w1_lo, F, E, 256, 32);
         wgt(mp.w_164[l], L.w1_hi, L.w1_lo, F, E, 64);
         wgt(mp.w_2[l], L.w2_hi, L.w2_lo, E, F, 256);
