@@ -203,6 +203,16 @@ int  tip_last_launch_count(const tip_model* m);
 /* Select the GEMM engine: 0 = auto (= 2), 1 = FFMA fp32 kernels (cross-check engine),
  * 2 = tcgen05 3xFP16-split tensor-core kernels. */
 int  tip_set_gemm_engine(tip_model* m, int engine);
+/* Kernel-selection knobs of the tcgen05 engine (initial values: TIP_* environment; results do not depend on them beyond
+ * fp32 round-off, every combination is parity-tested).  Keys:
+ *   "atm"           GEMMs that run on the A-operand-in-tensor-memory kernel (csrc/tip_umma_atm.cuh): bit mask 1 in_linear,
+ *                   2 qkv, 4 ff1, 8 rnn_ih; -1 (default) = all four on handles that are or own execution lanes, none otherwise
+ *   "atm_grid"      CTAs per such launch (0 = one per 128-row tile)
+ *   "atm_min_tiles" ... used for forwards of at least this many 128-row tiles (default 64)
+ *   "dyn_sched"     1: the plain GEMMs draw their tiles from a device counter instead of a static round-robin (default 0)
+ *   "ln_pair"       LayerNorm GEMMs with K >= value run on CTA pairs (cta_group::2); 0 (default) = never
+ * No reference counterpart (the reference has no kernels of its own). */
+int  tip_set_tuning(tip_model* m, const char* key, int value);
 /* CUDA-graph the forward for a fixed (B, L) (used by the streaming path); 0 disables. */
 int  tip_set_use_graphs(tip_model* m, int enable);
 /* Per-stage device timing of the forward (bench.py's roofline leg): when enabled, a CUDA event is

@@ -596,3 +596,68 @@ def test_b256_released_checkpoint_golden():
     # relative checksum (outputs reach |y| = 11 with these weights): mean signed error per element below 1e-6
     assert abs(y.astype(np.float64).sum() - float(g["y_sum"])) < 1e-6 * y.size + 0.5
 
+
+
+KNOBS = [dict(atm=15), dict(atm=15, atm_grid=148), dict(atm=15, atm_grid=37), dict(atm=5), dict(dyn_sched=1),
+         dict(ln_pair=512), dict(atm=15, dyn_sched=1, ln_pair=512)]
+
+
+@pytest.mark.parametrize("knobs", KNOBS, ids=["-".join(f"{k}{v}" for k, v in kn.items()) for kn in KNOBS])
+def test_kernel_selection_knobs_match_reference_and_oracle(knobs):
+    """tip_set_tuning: every kernel choice of the tcgen05 engine gives the reference's numbers.  "atm" = wide GEMMs on the
+    A-operand-in-tensor-memory kernel (tcgen05.cp + TS-mode MMAs; work split into contiguous runs of (row tile, n-tile)
+    pairs over atm_grid CTAs: 80 = one row tile each, 148 = runs that cross row tiles, 37 = several row tiles per CTA),
+    "dyn_sched" = the plain GEMMs draw tiles from a device counter, "ln_pair" = ff2 + LayerNorm on CTA pairs.
+    B = 256 (80 row tiles, the bench workload: golden from the reference module) and B = 205 (64.06 -> 65 row tiles: ragged
+    last tile, odd tile count) in deterministic mode, B = 256 as shipped (dropout in the ff1 epilogue of the new kernel)
+    mask for mask against the oracle; calls 2 and 3 of a shape are CUDA-graph capture and replay."""
+    g = np.load(os.path.join(GOLD, "rw_b256_l40_sub.npz"))
+    sd = O.random_state_dict(int(g["wseed"]))
+    m = make_model(sd, engine=2)
+    for k, v in knobs.items():
+        m.set_tuning(k, v)
+    x_imu, x_s = O.synth_inputs(int(g["xseed"]), 256, 40)
+    for _ in range(3):
+        y = run(m, x_imu, x_s)
+        assert np.abs(y[g["idx"]] - g["y_sub"]).max() < TOL
+        assert np.abs(y[:, -1] - g["y_last"]).max() < TOL
+        assert abs(y.astype(np.float64).sum() - float(g["y_sum"])) < 0.5
+    xi2, xs2 = O.synth_inputs(77, 205, 40, nan_frac=0.02)
+    ref2 = O.forward(sd, xi2, xs2)
+    for _ in range(3):
+        assert np.abs(run(m, xi2, xs2) - ref2).max() < TOL
+    m.train()
+    m.past_state_dropout = 0.8
+    xi, xs = torch.from_numpy(x_imu).cuda(), torch.from_numpy(x_s).cuda()
+    for tseed in (11, 12, 13):
+        seed = _seed_for(tseed)
+        y = m(xi, xs).cpu().numpy()
+        ref = O.forward(sd, x_imu, x_s, dropout=dict(seed=seed, past_state_dropout=0.8, encoder_dropout=0.1))
+        assert np.isfinite(y).all() and np.abs(y - ref).max() < 2 * TOL, (tseed, np.abs(y - ref).max())
+    with pytest.raises(RuntimeError):
+        m.set_tuning("no_such_knob", 1)
+
+
+def test_dynamic_scheduler_counters_rearm_across_launches_and_parts():
+    """The dynamic tile scheduler's device counters are re-armed by the last CTA of every launch: many back-to-back
+    forwards (eager, then graph replays), the two-part host entry (its parts run concurrently on two streams and use
+    disjoint counter slots) and a change of batch size all keep giving the single result."""
+    sd = O.random_state_dict(29)
+    m = make_model(sd, engine=2)
+    x_imu, x_s = O.synth_inputs(45, 256, 40)
+    want = run(m, x_imu, x_s)
+    m.set_tuning("dyn_sched", 1)
+    xi, xs = torch.from_numpy(x_imu).cuda(), torch.from_numpy(x_s).cuda()
+    for _ in range(12):
+        assert torch.equal(m(xi, xs).cpu(), torch.from_numpy(want))
+    hi, hs = torch.from_numpy(x_imu).pin_memory(), torch.from_numpy(x_s).pin_memory()
+    out = torch.empty((256, 40, 131)).pin_memory()
+    first = None
+    for _ in range(4):
+        m.forward_host(hi, hs, out=out)
+        assert float((out - torch.from_numpy(want)).abs().max()) < 2e-5      # (half-batch parts take other kernel paths: round-off)
+        first = out.clone() if first is None else first
+        assert torch.equal(out, first)
+    y = m(xi[:150], xs[:150]).cpu().numpy()
+    assert np.abs(y - want[:150]).max() < 2e-5
+    assert torch.equal(m(xi, xs).cpu(), torch.from_numpy(want))

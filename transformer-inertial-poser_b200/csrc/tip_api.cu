@@ -12,6 +12,7 @@
 #include "tip_attn_mma.cuh"
 #include "tip_qkv_attn.cuh"
 #include "tip_ffn_fused.cuh"
+#include "tip_umma_atm.cuh"
 
 using namespace tip;
 
@@ -65,11 +66,22 @@ static DropP drop_of(const tip_dropout* d) {
     return r;
 }
 
+constexpr int SCHED_SLOTS = 128;                                         // one per GEMM launch of a forward part (2 parts x 64)
+constexpr size_t SEED_SCHED_BYTES = sizeof(uint64_t) + SCHED_SLOTS * 2 * sizeof(int);
+
 struct tip_model {
     SharedWeights* sw = nullptr;
     bool is_lane = false;
+    bool laned = false;                 // this handle has lanes or is one: several forwards share the GPU (throughput mode)
+    // tuning knobs (tip_set_tuning; initial values from the TIP_* environment)
+    int tune_atm = -1;                  // GEMMs on the A-in-TMEM kernel: bit mask 1 in_linear, 2 qkv, 4 ff1, 8 rnn_ih; -1 = auto (all four when laned)
+    int tune_atm_grid = 0;              // CTAs per A-in-TMEM launch (0 = one per 128-row tile)
+    int tune_atm_min_tiles = 64;        // ... for forwards of at least this many row tiles
+    int tune_dyn_sched = 0;             // dynamic tile scheduler of the plain GEMMs
+    int tune_ln_pair = 0;               // LayerNorm GEMMs with K >= this on CTA pairs (0 = never)
     uint64_t pack_ordered_seq = 0;      // last pack this handle's streams are known to be ordered after (pack complete)
-    uint64_t* d_seed = nullptr;         // base seed of the current stochastic call (device memory; graphs read it)
+    uint64_t* d_seed = nullptr;         // base seed of the current stochastic call (device memory; graphs read it); followed by
+                                        // the {next tile, CTAs done} counter pairs of the GEMMs' dynamic tile scheduler (SCHED_SLOTS)
     tip_dims cdims{};
     Dims d{};
     PackOff off{};
@@ -158,6 +170,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static int quiesce_host_jobs(tip_model* m);      // wait until no pipelined host job still uses the workspace / weights
 
 // every captured graph bakes in workspace addresses, tensor maps and the engine choice
+static void init_tuning(tip_model* m);
 static void drop_graphs(tip_model* m) {
     if (m->st_graph) { cudaGraphExecDestroy(m->st_graph); m->st_graph = nullptr; }
     for (FwdGraph& g : m->fwd_graphs) {
@@ -239,10 +252,11 @@ extern "C" int tip_create(const tip_dims* dims, tip_model** out) {
     m->d.with_rnn = dims->with_rnn ? 1 : 0;
     m->d.khead = dims->with_rnn ? R : E;
     m->rnn_stream_fallback = getenv("TIP_RNN_STREAM") ? atoi(getenv("TIP_RNN_STREAM")) : 0;
+    init_tuning(m);
     compute_offsets(m);
     m->sw = new SharedWeights();
     cudaError_t e = cudaMalloc(&m->sw->blob, m->off.total * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_seed, sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_seed, SEED_SCHED_BYTES);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->sw->ev_pack, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         g_create_error = std::string("cudaMalloc(weights): ") + cudaGetErrorString(e);
@@ -254,7 +268,7 @@ extern "C" int tip_create(const tip_dims* dims, tip_model** out) {
     }
     m->blob = m->sw->blob;
     cudaMemset(m->blob, 0, m->off.total * sizeof(float));
-    cudaMemset(m->d_seed, 0, sizeof(uint64_t));
+    cudaMemset(m->d_seed, 0, SEED_SCHED_BYTES);
     *out = m;
     return TIP_OK;
 }
@@ -276,12 +290,15 @@ extern "C" int tip_create_lane(tip_model* owner, tip_model** out) {
     m->engine = owner->engine;
     m->rnn_stream_fallback = owner->rnn_stream_fallback;
     m->is_lane = true;
-    if (cudaMalloc(&m->d_seed, sizeof(uint64_t)) != cudaSuccess) {
+    init_tuning(m);
+    m->laned = true;
+    if (!owner->laned) { owner->laned = true; drop_graphs(owner); }      // (its captured forwards predate the throughput-mode kernel choice)
+    if (cudaMalloc(&m->d_seed, SEED_SCHED_BYTES) != cudaSuccess) {
         g_create_error = "cudaMalloc(seed) failed";
         delete m;
         return TIP_ERR_OOM;
     }
-    cudaMemset(m->d_seed, 0, sizeof(uint64_t));
+    cudaMemset(m->d_seed, 0, SEED_SCHED_BYTES);
     m->sw = owner->sw;
     m->sw->refs++;
     m->blob = m->sw->blob;
@@ -446,6 +463,26 @@ extern "C" int tip_pack_weights(tip_model* m, const float* const* t, const int64
     m->sw->pack_seq++;
     m->sw->packed = true;
     return TIP_OK;        // (addresses unchanged: tensor maps and captured graphs of every handle stay valid)
+}
+static void init_tuning(tip_model* m) {
+    auto env = [](const char* k, int dflt) { const char* v = getenv(k); return v ? atoi(v) : dflt; };
+    m->tune_atm = env("TIP_ATM", -1);
+    m->tune_atm_grid = env("TIP_ATM_GRID", 0);
+    m->tune_atm_min_tiles = env("TIP_ATM_MIN_TILES", 64);
+    m->tune_dyn_sched = env("TIP_DYN_SCHED", 0);
+    m->tune_ln_pair = env("TIP_LN_PAIR", 0);
+}
+extern "C" int tip_set_tuning(tip_model* m, const char* key, int value) {
+    if (!m || !key) return TIP_ERR_INVALID_ARG;
+    const std::string k(key);
+    if (k == "atm") m->tune_atm = value;
+    else if (k == "atm_grid") m->tune_atm_grid = value;
+    else if (k == "atm_min_tiles") m->tune_atm_min_tiles = value;
+    else if (k == "dyn_sched") m->tune_dyn_sched = value;
+    else if (k == "ln_pair") m->tune_ln_pair = value;
+    else { m->set_error("tip_set_tuning: unknown key '" + k + "'"); return TIP_ERR_INVALID_ARG; }
+    drop_graphs(m);                     // captured forwards have the old kernel choice baked in
+    return TIP_OK;
 }
 extern "C" int tip_set_gemm_engine(tip_model* m, int engine) {
     if (!m || engine < 0 || engine > 2) return TIP_ERR_INVALID_ARG;
@@ -813,13 +850,17 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
     float* lo_hid = umma ? m->hid + m->plane_f / 2 : nullptr;
     float* lo_hs = umma ? m->hs + m->plane_r / 2 : nullptr;
 
+    // TIP_SKIP (diagnostic, results become garbage): bit mask of stages NOT launched -- 1 condition, 2 in_linear, 4 qkv,
+    // 8 attention, 16 out_proj+LN, 32 ff1, 64 ff2+LN, 128 rnn_ih, 256 rnn, 512 head.  tools/lane_ablation.py times the
+    // laned forward with one stage removed at a time: the stage's MARGINAL cost when other lanes fill the machine.
+    static const int skip = getenv("TIP_SKIP") ? atoi(getenv("TIP_SKIP")) : 0;
     m->st_names.clear();
     m->st_layers.clear();
     mark(m, st, "condition");
     {
         const int nr = M - R0;
         const int64_t total = (int64_t)nr * (d.kin_pad / 8);
-        const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+        const int blocks = (skip & 1) ? 1 : (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
         float* xo = umma ? reinterpret_cast<float*>(reinterpret_cast<__half*>(m->xin) + (size_t)R0 * d.kin_pad) : m->xin + (size_t)R0 * d.kin_pad;
         float* xl = umma ? reinterpret_cast<float*>(reinterpret_cast<__half*>(lo_xin) + (size_t)R0 * d.kin_pad) : nullptr;
         pdl_kind() = 8;
@@ -829,6 +870,8 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
         m->launches++;
     }
     auto gemm = [&](int which, int layer, const float* A, int K, const float* Wp, int N, Epi ep, bool ln) {
+        if (skip & (which == UG_IN ? 2 : which == UG_QKV ? 4 : which == UG_OUT ? 16 : which == UG_FF1 ? 32 : which == UG_FF2 ? 64
+                    : which == UG_IH ? 128 : 512)) return;
         ep.seed_ptr = m->d_seed;
         ep.drop_thr = drop_threshold(ep.drop_p);
         ep.drop_inv = drop_inv_keep(ep.drop_p);
@@ -839,6 +882,9 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
             static const int dbg = getenv("TIP_DBG") ? atoi(getenv("TIP_DBG")) : 0;
             ep.dbg = dbg;
             ep.pdl_early = (M - R0 <= 1024) ? 1 : 0;
+            // dynamic tile scheduler of the plain GEMMs: one counter pair per launch of the forward (the host entry's second
+            // batch part, which runs concurrently on its own stream, uses the upper half of the slots)
+            ep.sched = (m->tune_dyn_sched && !ln) ? reinterpret_cast<int*>(m->d_seed + 1) + 2 * ((T0 > 0 ? 64 : 0) + (sc % 64)) : nullptr;
             ep.tbuf = nullptr;
             static const int ts_on = getenv("TIP_TS") ? atoi(getenv("TIP_TS")) : 0;
             if ((dbg & 4) || ts_on) {
@@ -854,6 +900,27 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
             // 328 vs 401 us, 32: 303 vs 373, 64: 321 vs 387, 96: 350 vs 412, 128: 393 vs 412, 192: 444 vs 459;
             // B = 256 (80 tiles = 320 CTAs = three waves): 549 vs 514, so the fused kernel keeps the big batches.
             static const int skinny_tiles = getenv("TIP_SKINNY_TILES") ? atoi(getenv("TIP_SKINNY_TILES")) : 74;
+            // A operand resident in tensor memory (tip_umma_atm.cuh): a CTA owns a contiguous run of (row tile, n-tile) pairs,
+            // keeps the row tile's A in TMEM and streams only W.  Knobs (tip_set_tuning / TIP_ATM, TIP_ATM_GRID,
+            // TIP_ATM_MIN_TILES): which GEMMs use it (bit mask 1 in_linear, 2 qkv, 4 ff1, 8 rnn_ih; auto = all four on handles
+            // that run as execution lanes, where its smaller footprint -- one CTA per row tile by default -- leaves SMs to the
+            // other lanes' kernels; a lone forward is faster on the plain kernel's 148 CTAs), CTAs per launch, minimum row tiles.
+            const int atm_mask = m->tune_atm >= 0 ? m->tune_atm : (m->laned ? 15 : 0);
+            const int atm_min_tiles = m->tune_atm_min_tiles, atm_grid = m->tune_atm_grid > 0 ? m->tune_atm_grid : TN;
+            const int atm_bit = which == UG_IN ? 1 : which == UG_QKV ? 2 : which == UG_FF1 ? 4 : which == UG_IH ? 8 : 0;
+            if (!ln && (atm_mask & atm_bit) && K == E && (N % AT_BN) == 0 && N <= AT_MAX_N_PER_UNIT && TN >= atm_min_tiles && !(dbg & 7)) {
+                const UmmaMaps& mp = m->maps;
+                const UmmaOperand& Am = which == UG_IN ? mp.a_xin : which == UG_FF1 ? mp.a_xb : mp.a_xa;
+                const UmmaOperand& Bm = which == UG_IN ? mp.w_in : which == UG_QKV ? mp.w_qkv[layer] : which == UG_FF1 ? mp.w_1[layer] : mp.w_ih;
+                const UmmaOutput& Cm = which == UG_IN ? mp.o_xa : which == UG_QKV ? mp.o_qkv : which == UG_FF1 ? mp.o_hid : mp.o_gi;
+                if (Cm.valid) {
+                    if (ep.tbuf) ep.tbuf = g_tbuf + 1024 + 64 * (which == UG_IN ? 0 : which == UG_QKV ? 1 : which == UG_FF1 ? 2 : 3);
+                    launch_atm_gemm(mp, Am, Bm, Cm, M, N, T0, TN, atm_grid, ep, st);
+                    m->launches++;
+                    return;
+                }
+            }
+            m->maps.ln_pair_min_k = m->tune_ln_pair;
             if (ln && TN <= skinny_tiles) {
                 Epi gp = ep;
                 gp.resid = gp.resid_lo = nullptr; gp.gamma = gp.beta = nullptr;
@@ -895,7 +962,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
         if (umma) ep.out_lo = m->qkv + (size_t)m->cap_rows * 3 * E / 2;     // FP16 planes for the mma attention
         gemm(UG_QKV, l, m->xa, E, W + Lo.wqkv, 3 * E, ep, false);
         mark(m, st, "attention", l);
-        launch_attention(m, st, m->qkv, m->att, lo_att, nw, L, p_enc, seed + seed_attn(l), R0);
+        if (!(skip & 8)) launch_attention(m, st, m->qkv, m->att, lo_att, nw, L, p_enc, seed + seed_attn(l), R0);
         }
         mark(m, st, "out_proj_ln", l);
         ep = Epi{}; ep.bias = W + Lo.bo; ep.resid = m->xa; ep.resid_lo = lo_xa; ep.ldr = E;
@@ -923,7 +990,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
         ep = Epi{}; ep.bias = W + o.brnn; ep.out = m->gi; ep.ldc = R;
         gemm(UG_IH, 0, m->xa, E, W + o.wih, R, ep, false);
         mark(m, st, "rnn");
-        launch_rnn(m, st, m->gi + (size_t)R0 * R, umma ? reinterpret_cast<float*>(reinterpret_cast<__half*>(m->hs) + (size_t)R0 * R) : m->hs,
+        if (!(skip & 256)) launch_rnn(m, st, m->gi + (size_t)R0 * R, umma ? reinterpret_cast<float*>(reinterpret_cast<__half*>(m->hs) + (size_t)R0 * R) : m->hs,
                    lo_hs ? reinterpret_cast<float*>(reinterpret_cast<__half*>(lo_hs) + (size_t)R0 * R) : nullptr, nw, L);
         mark(m, st, "head");
         head(UG_HEAD_R, m->hs, R);                                              // reference :102

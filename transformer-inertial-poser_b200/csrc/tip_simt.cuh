@@ -101,6 +101,7 @@ struct Epi {
     unsigned long long* tbuf;   // optional phase timestamps of CTA 0 (TIP_DBG & 4)
     int tma_out;            // tcgen05 engine: the output goes through TMA store boxes
     int pdl_early;          // programmatic dependent launch: trigger the next kernel at the start (small forwards) or at the end
+    int* sched;             // tcgen05 engine, plain tiles: {next tile, CTAs done} counters of the dynamic tile scheduler (null = static round-robin)
 };
 
 constexpr int SG_BK = 16;

@@ -43,7 +43,7 @@ template <int BN, int CG = 1, int BK = UM_BK> struct UmmaCfg {
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
     static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;   // double-buffered accumulator (power of two)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * 4096 /*epilogue staging*/ + 1024 /*align slack*/ +
-                                      192 /*barriers, seed slot*/ + 1024 /*LN row stats*/;
+                                      320 /*barriers, seed slot, tile-scheduler ring*/ + 1024 /*LN row stats*/;
 };
 
 namespace ptx {
@@ -267,7 +267,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     using Cfg = UmmaCfg<BN, CG, BK>;
     constexpr int STAGES = Cfg::STAGES;
     static_assert(BK == 64 || (BK == 32 && !LN && CG == 1), "64-byte k-blocks: plain single-CTA tiles only");
-    static_assert(CG == 1 || (CG == 2 && !LN && (BN == 256 || BN == 128)), "pair tiles: 256 x 256 or 256 x 128, no LayerNorm epilogue");
+    static_assert(CG == 1 || (CG == 2 && (BN == 256 || (BN == 128 && !LN))), "pair tiles: 256 x 256 (plain or LayerNorm) or 256 x 128 (plain)");
     // 128B-swizzled operand tiles need 1024-byte alignment.  The kernel has no static shared memory,
     // so the dynamic window starts at shared offset 0; keeping the pointer un-cast preserves the
     // shared address space (LDS/STS instead of generic LD/ST for the epilogue staging).
@@ -281,7 +281,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     uint64_t* rfull_bar = bars + 2 * STAGES + 5;  //           LN: residual tile landed in the ring (TMA -> epilogue)
-    float* row_stat = reinterpret_cast<float*>(bars + 2 * STAGES + 8);   // (16-byte aligned: float4 reads)   // LN: [2 halves][128 rows] partials, then mean/rstd
+    // dynamic tile scheduler (ep.sched != null; plain single-CTA tiles): the producer thread draws tile indices from a global
+    // counter and hands them to the MMA thread and the epilogue warps through a 4-deep ring.  With several execution lanes
+    // a kernel often starts on the SMs another lane's narrow kernel leaves free and gets the rest later: CTAs that are
+    // resident early then simply take more tiles (a static round-robin makes the kernel wait for its last CTA's share).
+    uint64_t* sfull_bar = bars + 2 * STAGES + 8;      // [4] producer -> consumers
+    uint64_t* sempty_bar = bars + 2 * STAGES + 12;    // [4] consumers (MMA thread + 8 epilogue warps) -> producer
+    volatile int* stile = reinterpret_cast<volatile int*>(bars + 2 * STAGES + 16);   // [4]
+    float* row_stat = reinterpret_cast<float*>(bars + 2 * STAGES + 20);   // (16-byte aligned: float4 reads)   // LN: [2 halves][128 rows] partials, then mean/rstd; plain: [2][256] bias slices
     // LN fast path (no dropout): after a tile's last k-block the operand ring is idle, so the producer parks the
     // residual tile there (128 KB, the same 64-column swizzled boxes the GEMMs read xa / xb with) and the
     // epilogue stages its output boxes in the ring's last 64 KB; both stages go back to the producer when the
@@ -294,6 +301,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
     const int num_kb = K / BK;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;   // rank 0 = leader: issues the pair's MMAs
     const int grp = blockIdx.x / CG, n_grp = gridDim.x / CG;   // persistent loop over tiles, one CTA group per tile
+    const bool dyn = (CG == 1 && !LN) && ep.sched != nullptr;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&mapA_hi); ptx::prefetch_tmap(&mapA_lo);
@@ -302,6 +310,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         // the accumulator of a pair is released by the epilogue warps of BOTH CTAs (on the leader's barrier)
         for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], UM_EPI_WARPS * CG); }
         ptx::mbar_init(rfull_bar, 1);
+        for (int s = 0; s < 4; ++s) { ptx::mbar_init(&sfull_bar[s], 1); ptx::mbar_init(&sempty_bar[s], 1 + UM_EPI_WARPS); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) { if constexpr (CG == 2) ptx::tmem_alloc2(tmem_slot, Cfg::TMEM_COLS); else ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS); }
@@ -323,7 +332,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
 #pragma unroll
             for (int s = 0; s < STAGES; ++s) uses[s] = 0;
             if constexpr (LN) { ptx::prefetch_tmap(&mapR_hi); ptx::prefetch_tmap(&mapR_lo); }
-            for (int tile = grp; tile < total_tiles; tile += n_grp) {
+            int tile = grp;
+            if (dyn) {                                  // first tile: drawn and published (ring slot 0 is free)
+                tile = atomicAdd(ep.sched, 1);
+                stile[0] = tile;
+                ptx::mbar_arrive(&sfull_bar[0]);
+            }
+            for (int pit = 0; tile < total_tiles; ++pit) {
+                int tile_next = tile + n_grp;
+                if (dyn) tile_next = atomicAdd(ep.sched, 1);       // in flight while this tile's loads are issued
                 const int m0 = (m_tile0 + (tile / n_tiles) * CG + (int)cta_rank) * UM_BM;
                 const int n0 = (tile % n_tiles) * BN + (int)cta_rank * Cfg::B_ROWS;      // this CTA's slice of the B tile
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -361,15 +378,30 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                         }
                     }
                 }
+                if (dyn) {                              // publish the next tile (or the end marker) to the consumers
+                    const int q = (pit + 1) & 3;
+                    ptx::mbar_wait(&sempty_bar[q], (((pit + 1) >> 2) & 1) ^ 1);
+                    stile[q] = tile_next;
+                    ptx::mbar_arrive(&sfull_bar[q]);
+                }
+                tile = tile_next;
             }
+            // the last CTA to run dry re-arms the counters for the next launch that uses this slot
+            if (dyn && atomicAdd(ep.sched + 1, 1) == (int)gridDim.x - 1) { ep.sched[0] = 0; ep.sched[1] = 0; }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0 && cta_rank == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(UM_BM * CG, BN);
             int stage = 0; uint32_t phase = 0;
-            int it = 0;
-            for (int tile = grp; tile < total_tiles; tile += n_grp, ++it) {
+            for (int it = 0;; ++it) {
+                int tile = grp + it * n_grp;
+                if (dyn) {
+                    ptx::mbar_wait(&sfull_bar[it & 3], (it >> 2) & 1);
+                    tile = stile[it & 3];
+                    ptx::mbar_arrive(&sempty_bar[it & 3]);
+                }
+                if (tile >= total_tiles) break;
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -420,8 +452,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
         // (constant bank, no registers), the site seed is parked in shared memory by the first epilogue thread --
         // the LayerNorm epilogue holds a 128-column row in registers and has none to spare
         volatile uint64_t* seed_slot = reinterpret_cast<volatile uint64_t*>(bars + 2 * STAGES + 6);
-        int it = 0;
-        for (int tile = grp; tile < total_tiles; tile += n_grp, ++it) {
+        for (int it = 0;; ++it) {
+            int tile = grp + it * n_grp;
+            if (dyn) {
+                ptx::mbar_wait(&sfull_bar[it & 3], (it >> 2) & 1);
+                tile = stile[it & 3];
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&sempty_bar[it & 3]);
+            }
+            if (tile >= total_tiles) break;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int m0 = (m_tile0 + (tile / n_tiles) * CG + (int)cta_rank) * UM_BM, n0 = (tile % n_tiles) * BN;
@@ -654,7 +693,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                     // the accumulator is in registers: hand the TMEM buffer back to the MMA warp now
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+                    if (lane == 0) {
+                        if constexpr (CG == 2) ptx::mbar_arrive_cluster(map_to_cta(ptx::smem_u32(&tempty_bar[as]), 0u));
+                        else ptx::mbar_arrive(&tempty_bar[as]);
+                    }
                     ptx::mbar_wait(rfull_bar, (uint32_t)(it & 1));    // residual tile landed (issued right after the last k-block)
                     float rsum = 0.f;
                     const uint8_t* rrow = smem + trow * 128;          // this row inside every 16 KB box
@@ -798,6 +840,7 @@ struct UmmaMaps {
     UmmaOperand a_xin, a_xa, a_xb, a_att, a_hid, a_hs;                    // activations (box 32 x 128)
     UmmaOperand w_in, w_qkv[MAX_LAYERS], w_o[MAX_LAYERS], w_1[MAX_LAYERS], w_2[MAX_LAYERS], w_ih, w_l;
     UmmaOperand w_qkv256[MAX_LAYERS], w_1256[MAX_LAYERS], w_ih256;        // 256-row boxes of the same planes (wide tiles)
+    UmmaOperand w_2h[MAX_LAYERS];                                          // W2, 128-row boxes: each CTA of a LayerNorm pair tile stages half of B
     UmmaOperand w_o64[MAX_LAYERS], w_264[MAX_LAYERS];                     // 64-row boxes (skinny-M LayerNorm GEMMs, 4 CTAs per row tile)
     UmmaOperand w_qkv64[MAX_LAYERS], w_164[MAX_LAYERS], w_ih64;           // 64-row boxes: each CTA of a 256 x 128 pair tile stages half of B
     UmmaOperand a_xa32, a_xb32, w_qkv256k32[MAX_LAYERS], w_1256k32[MAX_LAYERS];   // 32-column (64-byte, SWIZZLE_64B) k-blocks: 128 x 256 tiles with a 4-stage ring
@@ -808,6 +851,7 @@ struct UmmaMaps {
     UmmaOutput o_xa, o_xb, o_hid, o_qkv, o_gi;                             // TMA-store targets
     UmmaOperand w_hh;                                                      // resident A operand of the recurrence (box 64 x 64)
     int num_sms = 148;
+    int ln_pair_min_k = 0;                                                 // LayerNorm GEMMs with K >= this run on CTA pairs (0 = never)
     bool attrs_set = false;
 };
 
@@ -915,6 +959,7 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         wgt(mp.w_1256k32[l], L.w1_hi, L.w1_lo, F, E, 256, 32);
         wgt(mp.w_164[l], L.w1_hi, L.w1_lo, F, E, 64);
         wgt(mp.w_2[l], L.w2_hi, L.w2_lo, E, F, 256);
+        wgt(mp.w_2h[l], L.w2_hi, L.w2_lo, E, F, 128);
     }
     if (d.with_rnn) wgt(mp.w_ih, o.wih_hi, o.wih_lo, R, E, 128);
     if (d.with_rnn) wgt(mp.w_ih256, o.wih_hi, o.wih_lo, R, E, 256);
@@ -939,6 +984,8 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         cudaFuncSetAttribute(umma_gemm_kernel<192, false, false, 1, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<192, 1, 32>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<128, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 2>::SMEM_BYTES);
         cudaFuncSetAttribute(umma_gemm_kernel<128, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 2>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<256, true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256, 2>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_gemm_kernel<256, true, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256, 2>::SMEM_BYTES);
         mp.attrs_set = true;
     }
     return TIP_OK;
@@ -994,7 +1041,26 @@ inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, c
         launch_k(umma_gemm_kernel<64, false, false>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<64>::SMEM_BYTES, st, A->hi, A->lo, B64->hi, B64->lo, mp.o_pre.c0, mp.o_pre.c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
         return;
     }
-    if (ln) {
+    if (ln && which == UG_FF2 && mp.ln_pair_min_k > 0 && K >= mp.ln_pair_min_k && (m_tiles % 2) == 0 && m_tiles >= 32) {
+        // LayerNorm GEMM on CTA pairs (cta_group::2, 256 x 256 tiles): each CTA stages its own 128 rows of A and HALF of the
+        // weight k-block, so the bytes a CTA pulls through its L2 port per row tile drop from A + W to A + W / 2 (ff2:
+        // 1.77 -> 1.28 MB; the SM's port moves ~78 GB/s, which is what paces this kernel, not the MMAs)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * std::min(m_tiles / 2, mp.num_sms / 2));
+        cfg.blockDim = dim3(UM_THREADS);
+        cfg.dynamicSmemBytes = UmmaCfg<256, 2>::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        if (ep.drop_thr)
+            cudaLaunchKernelEx(&cfg, umma_gemm_kernel<256, true, true, 2, true>, A->hi, A->lo, mp.w_2h[layer].hi, mp.w_2h[layer].lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+        else
+            cudaLaunchKernelEx(&cfg, umma_gemm_kernel<256, true, true, 2>, A->hi, A->lo, mp.w_2h[layer].hi, mp.w_2h[layer].lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
+    } else if (ln) {
         const int tiles = m_tiles;                                // BN = 256 = the whole row
         if (ep.drop_thr)
             launch_k(umma_gemm_kernel<256, true, true, 1, true>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<256>::SMEM_BYTES, st, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);

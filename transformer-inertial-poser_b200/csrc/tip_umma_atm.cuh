@@ -1,0 +1,365 @@
+// GEMM variant with the A operand resident in TENSOR MEMORY: C[M, N] = A[M, 256] * W[N, 256]^T, N a multiple of 128.
+//
+// Why: with the 3-product FP16 split every k-step of a 128 x 128 tile reads 3 x (A 4 KB + B 4 KB) of operands from shared
+// memory -- 24 KB per 192 tensor-pipe clocks = the SM's whole 128 B/clk -- while TMA writes the next stages into the
+// same memory, and every 128 x 128 tile pulls 256 KB of operands through L2 (at 148 SMs that is the chip's L2 cap,
+// DESIGN 8).  For the wide GEMMs of the path (in_linear, qkv, ff1, rnn_ih: K = 256, N = 256 .. 1024) a work unit here is a
+// 128-row tile x a run of 128-column tiles:
+//   * the A tile (128 x 256, FP16 hi + lo = 128 KB) is loaded ONCE per unit -- TMA into the operand ring, then
+//     `tcgen05.cp` (shared -> tensor memory, 128 lanes x 256 bit per instruction, the same swizzled K-major descriptors an
+//     SS MMA would read) into 256 columns of tensor memory -- and feeds `tcgen05.mma` with A in TMEM for all of the
+//     unit's n-tiles;
+//   * only W is streamed afterwards (TMA, 128B-swizzled 64-wide k-blocks, 4-stage ring): half the shared-memory reads
+//     per MMA and up to 44 % fewer operand bytes from L2.
+// Work split: the (row tile, n-tile) pairs of the GEMM in row-major order are cut into gridDim.x contiguous runs of
+// (nearly) equal length, one per CTA, so all SMs are busy although M / 128 is smaller than the SM count; a run that crosses
+// into the next row tile reloads A there (at most two A loads per CTA in the shapes of the path).
+// Accumulators: two 128-column TMEM buffers (the epilogue of n-tile i overlaps the MMAs of n-tile i + 1; an accumulator is
+// released as soon as it sits in registers).  Epilogue = bias / ReLU / dropout / FP16 hi-lo split or fp32, 32 x 32 boxes
+// through four rotating 2 KB shared tiles per warp, written by TMA stores.
+#pragma once
+#include "tip_umma.cuh"
+
+namespace tip {
+
+constexpr int AT_BN = 128;
+constexpr int AT_PLANE_BYTES = 128 * 128;                  // one plane of a k-block: 128 rows x 128 B (A or W)
+constexpr int AT_STAGE_BYTES = 2 * AT_PLANE_BYTES;         // hi + lo = 32 KB
+constexpr int AT_MAX_N_PER_UNIT = 1024;
+// STAGES = depth of the operand ring (4 .. 6).  The W feed is latency-bound (throughput = bytes in flight / ~2.5 us under load),
+// so the ring gets the shared memory; per epilogue warp 8 KB of output staging (chunk outputs double-buffered) up to 5
+// stages, 4 KB with 6.
+template <int STAGES> struct AtmCfg {
+    static constexpr int STG_WARP_BYTES = STAGES >= 6 ? 4096 : 8192;
+    static constexpr int NBUF = STG_WARP_BYTES / 4096;     // 4 KB = one chunk's output (fp16 hi + lo tiles, or one fp32 tile)
+    static constexpr int SMEM_BYTES = STAGES * AT_STAGE_BYTES + UM_EPI_WARPS * STG_WARP_BYTES + 2 * AT_BN * 4 /*bias slices*/ + 256 /*barriers*/;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+constexpr int AT_TMEM_COLS = 512;                          // [0,128) / [128,256) accumulators, [256,384) A hi, [384,512) A lo
+constexpr int AT_A_COL0 = 256;
+
+namespace ptx {
+// shared -> tensor memory: 128 lanes x 256 bit (lane = row of a K-major tile, 16 fp16 = 8 columns)
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+}  // namespace ptx
+
+template <bool OUT_HALF, int AT_STAGES>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+umma_atm_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                     const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+                     const __grid_constant__ CUtensorMap mapC0, const __grid_constant__ CUtensorMap mapC1,
+                     int M, int N, int m_tile0, int m_tiles, Epi ep) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
+    using Cfg = AtmCfg<AT_STAGES>;
+    uint8_t* staging = smem + AT_STAGES * AT_STAGE_BYTES;                                  // 8 x (8 | 4) KB
+    float* sbias = reinterpret_cast<float*>(staging + UM_EPI_WARPS * Cfg::STG_WARP_BYTES); // [2][128]: this and the next n-tile's slice
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 2 * AT_BN);
+    uint64_t* full_bar = bars;                       // [STAGES] TMA -> MMA
+    uint64_t* empty_bar = bars + AT_STAGES;          // [STAGES] MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * AT_STAGES;      // [2] MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * AT_STAGES + 2; // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AT_STAGES + 4);
+    volatile uint64_t* seed_slot = reinterpret_cast<volatile uint64_t*>(bars + 2 * AT_STAGES + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int num_kb = E / UM_BK;                // 4 k-blocks of 64
+    // this CTA's run [u0, u1) of (row tile, n-tile) pairs, u = mt * n_tiles + nt
+    const int n_tiles = N / AT_BN;
+    const int total = m_tiles * n_tiles;
+    const int u0 = (int)(((long long)blockIdx.x * total) / gridDim.x);
+    const int u1 = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&mapA_hi); ptx::prefetch_tmap(&mapA_lo);
+        ptx::prefetch_tmap(&mapB_hi); ptx::prefetch_tmap(&mapB_lo);
+        for (int s = 0; s < AT_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], UM_EPI_WARPS); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, AT_TMEM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();
+    if (ep.pdl_early) griddep_launch();
+#define AT_TS(i) do { if (ep.tbuf && blockIdx.x == 0 && lane == 0) ep.tbuf[i] = ptx::globaltimer_ns(); } while (0)
+    if (warp == 2) AT_TS(0);
+
+    if (warp == 0) {
+        // ================= TMA producer: the A tile's four k-blocks, then W for every n-tile of the unit =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = u0; u < u1; ++u) {
+                const int mt = u / n_tiles, nt = u - mt * n_tiles;
+                if (u == u0 || nt == 0) {                       // a new row tile: its A k-blocks go through the ring first
+                    const int m0 = (m_tile0 + mt) * UM_BM;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        uint8_t* s = smem + stage * AT_STAGE_BYTES;
+                        ptx::mbar_expect_tx(&full_bar[stage], AT_STAGE_BYTES);
+                        ptx::tma_load_2d(s, &mapA_hi, &full_bar[stage], kb * UM_BK, m0);
+                        ptx::tma_load_2d(s + AT_PLANE_BYTES, &mapA_lo, &full_bar[stage], kb * UM_BK, m0);
+                        if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint8_t* s = smem + stage * AT_STAGE_BYTES;
+                    ptx::mbar_expect_tx(&full_bar[stage], AT_STAGE_BYTES);
+                    ptx::tma_load_2d(s, &mapB_hi, &full_bar[stage], kb * UM_BK, nt * AT_BN);
+                    ptx::tma_load_2d(s + AT_PLANE_BYTES, &mapB_lo, &full_bar[stage], kb * UM_BK, nt * AT_BN);
+                    if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer: A shared -> tensor memory, then A from tensor memory x W from the ring =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(UM_BM, AT_BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int u = u0; u < u1; ++u, ++it) {
+                const int nt = u % n_tiles;
+                if (u == u0 || nt == 0) {
+                    // A tile: shared -> tensor memory (tcgen05.cp runs in issue order behind the MMAs that still read the
+                    // previous row tile's A)
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        if (u == u0 && kb == 0) AT_TS(1);
+                        ptx::tc_fence_after();
+                        const uint32_t sa = ptx::smem_u32(smem + stage * AT_STAGE_BYTES);
+                        const uint64_t a_hi = umma_smem_desc(sa), a_lo = umma_smem_desc(sa + AT_PLANE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < UM_BK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            const uint32_t col = (uint32_t)(AT_A_COL0 + kb * 32 + k * 8);           // 16 k = 8 columns
+                            ptx::tmem_cp_128x256b(tmem_base + col, a_hi + adv);
+                            ptx::tmem_cp_128x256b(tmem_base + col + 128u, a_lo + adv);
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);               // slot free once the copies have read it
+                        if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    if (u == u0) AT_TS(2);
+                }
+                const int as = it & 1;
+                ptx::mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
+                if (it < 8) AT_TS(40 + it);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * AT_BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    if (it == 0 && kb == 0) AT_TS(3);
+                    ptx::tc_fence_after();
+                    const uint32_t sb = ptx::smem_u32(smem + stage * AT_STAGE_BYTES);
+                    const uint64_t b_hi = umma_smem_desc(sb), b_lo = umma_smem_desc(sb + AT_PLANE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < UM_BK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                        const uint32_t ah = tmem_base + (uint32_t)(AT_A_COL0 + kb * 32 + k * 8);
+                        const uint32_t al = ah + 128u;
+                        ptx::umma_f16_ts(d_tmem, al, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                        ptx::umma_f16_ts(d_tmem, ah, b_lo + adv, idesc, 1u);
+                        ptx::umma_f16_ts(d_tmem, ah, b_hi + adv, idesc, 1u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                ptx::umma_commit(&tfull_bar[as]);
+                if (it < 8) AT_TS(4 + it);
+            }
+        }
+    } else {
+        // ================= warps 2..9: epilogue; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =================
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const float asc = ep.acc_scale ? __ldg(ep.acc_scale) : 1.f;
+        const float osc = OUT_HALF ? ACT_SCALE : 1.f;
+        const float dinv = ep.drop_thr ? ep.drop_inv : 1.f;
+        const float relu_floor = ep.relu ? 0.f : -INFINITY;
+        const float sc = asc * osc * dinv;
+        uint8_t* sbuf = staging + (warp - 2) * Cfg::STG_WARP_BYTES;
+        // bias slice of an n-tile (pre-multiplied by the output scale [and 1/(1-p)]): fetched one tile ahead into a register,
+        // parked in the [2][128] shared slices at the top of its tile
+        const int et = (int)threadIdx.x - 64;
+        float bnext = (et < AT_BN && u0 < u1) ? __ldg(ep.bias + (u0 % n_tiles) * AT_BN + et) * osc * dinv : 0.f;
+        if (et == 0) *seed_slot = ep.drop_thr ? site_seed(ep.seed_ptr, ep.seed) : 0ull;
+        int it = 0;
+        for (int u = u0; u < u1; ++u, ++it) {
+            const int as = it & 1;
+            const int mt = u / n_tiles, nt = u - mt * n_tiles;
+            const int n0 = nt * AT_BN;
+            const int rbase = (m_tile0 + mt) * UM_BM + quarter * 32;
+            if (et < AT_BN) {
+                sbias[as * AT_BN + et] = bnext;
+                if (u + 1 < u1) bnext = __ldg(ep.bias + ((u + 1) % n_tiles) * AT_BN + et) * osc * dinv;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // (slice `as` was last read two tiles ago: every warp is past that)
+            ptx::mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+            if (warp == 2 && it < 8) AT_TS(12 + it);
+            ptx::tc_fence_after();
+            const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * AT_BN + half * 64);
+            float v[2][32];
+            ptx::tmem_ld32_nowait(t_acc, v[0]);
+            ptx::tmem_ld32_nowait(t_acc + 32, v[1]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);          // the accumulator sits in registers: hand it back
+            if (warp == 2 && it < 8) AT_TS(20 + it);
+            const float* bs = sbias + as * AT_BN + half * 64;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int colb = n0 + half * 64 + c * 32;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b = *reinterpret_cast<const float4*>(bs + c * 32 + 4 * j4);       // broadcast
+                    v[c][4 * j4 + 0] = fmaxf(fmaf(v[c][4 * j4 + 0], sc, b.x), relu_floor);
+                    v[c][4 * j4 + 1] = fmaxf(fmaf(v[c][4 * j4 + 1], sc, b.y), relu_floor);
+                    v[c][4 * j4 + 2] = fmaxf(fmaf(v[c][4 * j4 + 2], sc, b.z), relu_floor);
+                    v[c][4 * j4 + 3] = fmaxf(fmaf(v[c][4 * j4 + 3], sc, b.w), relu_floor);
+                }
+                if (ep.drop_thr) {                                      // dropout on the output (ff1): element index = row * N + col
+                    const uint64_t g0 = ((uint64_t)(rbase + lane) * N + colb) >> 2;
+                    const uint64_t dseed = *seed_slot;
+                    const uint32_t thr_hi = ep.drop_thr << 16;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const uint64_t h = hash_u64(dseed, g0 + j4);
+                        const uint32_t hl = (uint32_t)h, hh = (uint32_t)(h >> 32);
+                        if ((hl << 16) < thr_hi) v[c][4 * j4 + 0] = 0.f;
+                        if (hl < thr_hi) v[c][4 * j4 + 1] = 0.f;
+                        if ((hh << 16) < thr_hi) v[c][4 * j4 + 2] = 0.f;
+                        if (hh < thr_hi) v[c][4 * j4 + 3] = 0.f;
+                    }
+                }
+                if constexpr (OUT_HALF) {
+                    // [32 rows][64 B] tiles (hi, lo) of chunk c, 64B-swizzled: 16-byte chunk ^= (row >> 1) & 3.  Four tiles per
+                    // warp in rotation (c0 hi, c0 lo, c1 hi, c1 lo), one bulk group each: a tile is rewritten four groups later
+                    const int sw = (lane >> 1) & 3;
+                    uint4 uh[4], ul[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float h0, h1, l0, l1;
+                        __half2 t;
+                        veltkamp11(v[c][8 * j + 0], h0, l0); veltkamp11(v[c][8 * j + 1], h1, l1);
+                        t = __floats2half2_rn(h0, h1); uh[j].x = *reinterpret_cast<uint32_t*>(&t);
+                        t = __floats2half2_rn(l0, l1); ul[j].x = *reinterpret_cast<uint32_t*>(&t);
+                        veltkamp11(v[c][8 * j + 2], h0, l0); veltkamp11(v[c][8 * j + 3], h1, l1);
+                        t = __floats2half2_rn(h0, h1); uh[j].y = *reinterpret_cast<uint32_t*>(&t);
+                        t = __floats2half2_rn(l0, l1); ul[j].y = *reinterpret_cast<uint32_t*>(&t);
+                        veltkamp11(v[c][8 * j + 4], h0, l0); veltkamp11(v[c][8 * j + 5], h1, l1);
+                        t = __floats2half2_rn(h0, h1); uh[j].z = *reinterpret_cast<uint32_t*>(&t);
+                        t = __floats2half2_rn(l0, l1); ul[j].z = *reinterpret_cast<uint32_t*>(&t);
+                        veltkamp11(v[c][8 * j + 6], h0, l0); veltkamp11(v[c][8 * j + 7], h1, l1);
+                        t = __floats2half2_rn(h0, h1); uh[j].w = *reinterpret_cast<uint32_t*>(&t);
+                        t = __floats2half2_rn(l0, l1); ul[j].w = *reinterpret_cast<uint32_t*>(&t);
+                    }
+                    uint8_t* th = sbuf + (Cfg::NBUF == 2 ? c * 4096 : 0);
+                    uint8_t* tl = th + 2048;
+                    if constexpr (Cfg::NBUF == 2) {
+                        // four tiles per warp in rotation (c0 hi, c0 lo, c1 hi, c1 lo), one bulk group each
+                        if (lane == 0) ptx::bulk_wait_read<2>();          // hi AND lo tile of this chunk's previous use have been read
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(th + lane * 64 + ((j ^ sw) << 4)) = uh[j];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(tl + lane * 64 + ((j ^ sw) << 4)) = ul[j];
+                        ptx::fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&mapC0, th, colb, rbase);
+                            ptx::bulk_commit();
+                            ptx::tma_store_2d(&mapC1, tl, colb, rbase);
+                            ptx::bulk_commit();
+                        }
+                    } else {
+                        // two tiles (hi, lo): while one plane's box is still being read out the other can be rewritten
+                        if (lane == 0) ptx::bulk_wait_read<1>();          // hi tile free
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(th + lane * 64 + ((j ^ sw) << 4)) = uh[j];
+                        ptx::fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&mapC0, th, colb, rbase);
+                            ptx::bulk_commit();
+                            ptx::bulk_wait_read<1>();                     // lo tile free
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(tl + lane * 64 + ((j ^ sw) << 4)) = ul[j];
+                        ptx::fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&mapC1, tl, colb, rbase);
+                            ptx::bulk_commit();
+                        }
+                    }
+                } else {
+                    uint8_t* tf = sbuf + (Cfg::NBUF == 2 ? c * 4096 : 0);   // one [32 rows][128 B] fp32 tile per chunk, 128B-swizzled
+                    if (lane == 0) ptx::bulk_wait_read<Cfg::NBUF - 1>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(tf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                            make_float4(v[c][4 * j], v[c][4 * j + 1], v[c][4 * j + 2], v[c][4 * j + 3]);
+                    ptx::fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&mapC0, tf, colb, rbase);
+                        ptx::bulk_commit();
+                    }
+                }
+            }
+            if (warp == 2 && it < 8) AT_TS(28 + it);
+        }
+    }
+    if (!ep.pdl_early) griddep_launch();
+    if (warp >= 2 && lane == 0) ptx::bulk_wait0();
+    if (warp == 2) AT_TS(36);
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, AT_TMEM_COLS);
+    }
+}
+
+// grid_cap: CTAs of the launch (<= 0: one per SM); the (row tile, n-tile) pairs are dealt to them in contiguous runs
+template <int STAGES>
+inline void launch_atm_gemm_s(const UmmaMaps& mp, const UmmaOperand& A, const UmmaOperand& B, const UmmaOutput& C,
+                              int M, int N, int m_tile0, int m_tiles, int grid_cap, const Epi& ep, cudaStream_t st) {
+    static bool attrs = false;
+    if (!attrs) {
+        cudaFuncSetAttribute(umma_atm_gemm_kernel<true, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtmCfg<STAGES>::SMEM_BYTES);
+        cudaFuncSetAttribute(umma_atm_gemm_kernel<false, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtmCfg<STAGES>::SMEM_BYTES);
+        attrs = true;
+    }
+    pdl_kind() = 1;
+    const dim3 grid(std::min(grid_cap > 0 ? grid_cap : mp.num_sms, m_tiles * (N / AT_BN)));
+    if (ep.out_lo)
+        launch_k(umma_atm_gemm_kernel<true, STAGES>, grid, dim3(UM_THREADS), AtmCfg<STAGES>::SMEM_BYTES, st, A.hi, A.lo, B.hi, B.lo, C.c0, C.c1, M, N, m_tile0, m_tiles, ep);
+    else
+        launch_k(umma_atm_gemm_kernel<false, STAGES>, grid, dim3(UM_THREADS), AtmCfg<STAGES>::SMEM_BYTES, st, A.hi, A.lo, B.hi, B.lo, C.c0, C.c1, M, N, m_tile0, m_tiles, ep);
+}
+inline void launch_atm_gemm(const UmmaMaps& mp, const UmmaOperand& A, const UmmaOperand& B, const UmmaOutput& C,
+                            int M, int N, int m_tile0, int m_tiles, int grid_cap, const Epi& ep, cudaStream_t st) {
+    static const int stages = getenv("TIP_ATM_STAGES") ? atoi(getenv("TIP_ATM_STAGES")) : 5;
+    if (stages >= 6) launch_atm_gemm_s<6>(mp, A, B, C, M, N, m_tile0, m_tiles, grid_cap, ep, st);
+    else if (stages == 5) launch_atm_gemm_s<5>(mp, A, B, C, M, N, m_tile0, m_tiles, grid_cap, ep, st);
+    else launch_atm_gemm_s<4>(mp, A, B, C, M, N, m_tile0, m_tiles, grid_cap, ep, st);
+}
+
+}  // namespace tip

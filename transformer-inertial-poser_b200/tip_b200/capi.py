@@ -62,6 +62,7 @@ SIGNATURES = {
                                        C.POINTER(C.c_double)]),
     "tip_last_launch_count": (C.c_int, [_VP]),
     "tip_set_gemm_engine": (C.c_int, [_VP, C.c_int]),
+    "tip_set_tuning": (C.c_int, [_VP, C.c_char_p, C.c_int]),
     "tip_set_use_graphs": (C.c_int, [_VP, C.c_int]),
     "tip_set_profile": (C.c_int, [_VP, C.c_int]),
     "tip_profile_stages": (C.c_int, [_VP]),

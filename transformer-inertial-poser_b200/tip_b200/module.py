@@ -364,6 +364,13 @@ class TF_RNN_Past_State(nn.Module):
         h = self._ensure(dev)
         capi.check(self._lib, h, self._lib.tip_set_gemm_engine(h, int(engine)), "tip_set_gemm_engine")
 
+    def set_tuning(self, key: str, value: int):
+        """Kernel-selection knob of the tcgen05 engine (tip_set_tuning): "atm", "atm_grid", "atm_min_tiles", "dyn_sched",
+        "ln_pair"; see include/tip_b200.h.  Per handle: lanes made by make_lane() have their own."""
+        dev = next(self.parameters()).device
+        h = self._ensure(dev)
+        capi.check(self._lib, h, self._lib.tip_set_tuning(h, key.encode(), int(value)), "tip_set_tuning")
+
     def set_use_graphs(self, enable: bool):
         """CUDA-graph replay of repeated forwards / streaming frames (tip_set_use_graphs); on by default."""
         dev = next(self.parameters()).device
