@@ -400,7 +400,7 @@ def main():
     ap.add_argument("--profile-run", action="store_true",
                     help="for ncu launch lists: exactly W warm-up steps (forwards stay eager until a graph is captured), "
                          "no streaming / consumer / CPU-baseline legs")
-    ap.add_argument("--lanes", type=int, default=3, help="execution lanes (concurrent whole-batch forwards)")
+    ap.add_argument("--lanes", type=int, default=5, help="execution lanes (concurrent whole-batch forwards)")
     ap.add_argument("--e2e-depth", type=int, default=0, help="jobs in flight in the e2e leg's host pipeline (0: 2 per lane)")
     ap.add_argument("--repeats", type=int, default=5, help="the K-step timed region is repeated; the median region is reported")
     args = ap.parse_args()
@@ -509,6 +509,10 @@ def main():
 
     # ---- the same K steps one at a time on one lane, L2 flushed before each, per-step CUDA events: the latency of
     #      ONE forward (what the roofline legs below are stated against) ------------------------------------------
+    # (a handle that owns lanes picks the narrow throughput-mode kernels by itself; a lone forward is faster on the
+    #  full-width ones, which is what a handle without lanes runs: select them for this leg)
+    model.set_tuning("atm", 0)
+    model.set_tuning("ln_grid", 0)
     for i in range(2 if args.profile_run else 2 * n_sets):
         model(*sets[i % n_sets], out=outs[0])
     barrier()
@@ -522,6 +526,13 @@ def main():
     sampler.join()
     barrier()
     single_ms = reduce_([float(np.median([a.elapsed_time(b) for a, b in ev]))], MAX)[0]
+
+    def lone_kernels(on):
+        # a handle that owns lanes picks the narrow throughput-mode kernels by itself (-1 = auto); the one-forward-at-a-time
+        # legs (single_lane, the per-stage roofline pass) run the full-width kernels a handle without lanes uses
+        model.set_tuning("atm", 0 if on else -1)
+        model.set_tuning("ln_grid", 0 if on else -1)
+    lone_kernels(False)
 
     # ---- as shipped (the reference consumers' default: train mode, fresh Dropout(0.8) on the past state per call):
     #      the same K steps over the same lanes, every step with its own seed; graphs replay (seed in device memory) ---
@@ -572,6 +583,7 @@ def main():
     # ---- per-stage device times (roofline leg): a separate pass with an event before every kernel, same
     #      inputs, L2 flushed; outside the timed region because the per-kernel events perturb it ------------
     stage_ms = {}
+    lone_kernels(True)
     model.set_profile(True)
     for i in range(min(args.steps, 24)):
         flush.zero_()
@@ -579,6 +591,7 @@ def main():
         for name, layer, ms in model.profile():
             stage_ms.setdefault(name, []).append(ms)
     model.set_profile(False)
+    lone_kernels(False)
     barrier()
 
     # ---- e2e: the C-ABI host-buffer entries, pinned host buffers, every step = H2D of that step's inputs +
@@ -834,7 +847,10 @@ def main():
         "3-product FP16 split (3 MMAs per product), so the reachable ceiling is peak/3",
         "us_per_launch": per_launch[dom] * 1e3, "share_of_step": totals[dom] / tot_stage if tot_stage else None,
         "stage_timing": "separate pass with a CUDA event before every kernel (graph replay off), L2 flushed; the events add "
-                        "~4 us per kernel, so the stage sum exceeds single_lane.ms_per_step; kernels timed alone (one lane)",
+                        "~4 us per kernel, so the stage sum exceeds single_lane.ms_per_step; kernels timed alone (one lane, the "
+                        "full-width kernels of a handle without lanes; the laned headline runs the wide GEMMs on the A-in-TMEM "
+                        "kernel and the LayerNorm GEMMs with one CTA per two row tiles -- narrower, longer launches that pack "
+                        "better across lanes -- see throughput_mode)",
         "stage_us_per_forward": {k: round(v * 1e3, 2) for k, v in sorted(totals.items(), key=lambda kv: -kv[1])},
         "kernels": kernels,
         "forward_hbm": {"bound": "hbm", "achieved": fwd_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -861,6 +877,9 @@ def main():
                              f"(all regions in timed_regions_ms); step i is one whole-batch forward on lane i % {NL} ({NL} handles "
                              "sharing the parameters and the packed weights, own workspace and stream), each replayed as a CUDA graph (25 kernels)",
                    "lanes": NL, "cpus_bound_to_this_gpu": n_aff,
+                   "throughput_mode": "handles that own / are lanes choose by themselves (tip_set_tuning auto): in_linear, qkv, ff1, "
+                                      "rnn_ih on the A-operand-in-tensor-memory GEMM with one CTA per two 128-row tiles, fused "
+                                      "LayerNorm GEMMs with one CTA per two row tiles; same arithmetic, bit-identical outputs",
                    "engine": {0: "auto (tcgen05 3xFP16 split)", 1: "ffma", 2: "tcgen05-3xfp16"}[args.engine]},
         "timed_regions_ms": [round(r, 4) for r in regions],
         "timed_region_spread": (max(regions) - min(regions)) / dev_ms if dev_ms else None,

@@ -207,10 +207,13 @@ int  tip_set_gemm_engine(tip_model* m, int engine);
  * fp32 round-off, every combination is parity-tested).  Keys:
  *   "atm"           GEMMs that run on the A-operand-in-tensor-memory kernel (csrc/tip_umma_atm.cuh): bit mask 1 in_linear,
  *                   2 qkv, 4 ff1, 8 rnn_ih; -1 (default) = all four on handles that are or own execution lanes, none otherwise
- *   "atm_grid"      CTAs per such launch (0 = one per 128-row tile)
+ *   "atm_grid"      CTAs per such launch (0 = one per two 128-row tiles)
  *   "atm_min_tiles" ... used for forwards of at least this many 128-row tiles (default 64)
  *   "dyn_sched"     1: the plain GEMMs draw their tiles from a device counter instead of a static round-robin (default 0)
  *   "ln_pair"       LayerNorm GEMMs with K >= value run on CTA pairs (cta_group::2); 0 (default) = never
+ *   "ln_grid"       CTAs per fused-LayerNorm GEMM launch: 0 = one per 128-row tile, -1 (default) = that for a lone handle, one
+ *                   per two row tiles on handles that are or own execution lanes (narrow kernels pack better across lanes)
+ *   "rnn_clusters"  8-CTA clusters per tensor-core recurrence launch (0 = default: one per 20 windows)
  * No reference counterpart (the reference has no kernels of its own). */
 int  tip_set_tuning(tip_model* m, const char* key, int value);
 /* CUDA-graph the forward for a fixed (B, L) (used by the streaming path); 0 disables. */

@@ -75,10 +75,12 @@ struct tip_model {
     bool laned = false;                 // this handle has lanes or is one: several forwards share the GPU (throughput mode)
     // tuning knobs (tip_set_tuning; initial values from the TIP_* environment)
     int tune_atm = -1;                  // GEMMs on the A-in-TMEM kernel: bit mask 1 in_linear, 2 qkv, 4 ff1, 8 rnn_ih; -1 = auto (all four when laned)
-    int tune_atm_grid = 0;              // CTAs per A-in-TMEM launch (0 = one per 128-row tile)
+    int tune_atm_grid = 0;              // CTAs per A-in-TMEM launch (0 = one per two 128-row tiles)
     int tune_atm_min_tiles = 64;        // ... for forwards of at least this many row tiles
     int tune_dyn_sched = 0;             // dynamic tile scheduler of the plain GEMMs
     int tune_ln_pair = 0;               // LayerNorm GEMMs with K >= this on CTA pairs (0 = never)
+    int tune_ln_grid = -1;              // CTAs per fused-LayerNorm GEMM launch (0 = one per 128-row tile; -1 = auto: one per two row tiles when laned)
+    int tune_rnn_clusters = 0;          // 8-CTA clusters per tensor-core recurrence launch (0 = as many as the batch needs / the GPU co-schedules)
     uint64_t pack_ordered_seq = 0;      // last pack this handle's streams are known to be ordered after (pack complete)
     uint64_t* d_seed = nullptr;         // base seed of the current stochastic call (device memory; graphs read it); followed by
                                         // the {next tile, CTAs done} counter pairs of the GEMMs' dynamic tile scheduler (SCHED_SLOTS)
@@ -471,6 +473,8 @@ static void init_tuning(tip_model* m) {
     m->tune_atm_min_tiles = env("TIP_ATM_MIN_TILES", 64);
     m->tune_dyn_sched = env("TIP_DYN_SCHED", 0);
     m->tune_ln_pair = env("TIP_LN_PAIR", 0);
+    m->tune_ln_grid = env("TIP_LN_GRID", -1);
+    m->tune_rnn_clusters = env("TIP_RNN_UMMA_CLUSTERS", 0);
 }
 extern "C" int tip_set_tuning(tip_model* m, const char* key, int value) {
     if (!m || !key) return TIP_ERR_INVALID_ARG;
@@ -480,6 +484,8 @@ extern "C" int tip_set_tuning(tip_model* m, const char* key, int value) {
     else if (k == "atm_min_tiles") m->tune_atm_min_tiles = value;
     else if (k == "dyn_sched") m->tune_dyn_sched = value;
     else if (k == "ln_pair") m->tune_ln_pair = value;
+    else if (k == "ln_grid") m->tune_ln_grid = value;
+    else if (k == "rnn_clusters") m->tune_rnn_clusters = value;
     else { m->set_error("tip_set_tuning: unknown key '" + k + "'"); return TIP_ERR_INVALID_ARG; }
     drop_graphs(m);                     // captured forwards have the old kernel choice baked in
     return TIP_OK;
@@ -761,9 +767,12 @@ static void launch_rnn(tip_model* m, cudaStream_t st, const float* gi, float* hs
                 launch_k(rnn_umma_kernel<true>, dim3(nc * RU_CTAS), dim3(RU_THREADS), RU_SMEM_BYTES, st,
                     m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
                     m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf, wh, wl);
-            else if (pipe && nw20 && (B + 19) / 20 <= m->rnn_umma_clusters)
-                // the batch fits the co-resident clusters with 20 windows each: smaller all-gather per step
-                launch_k(rnn_umma_kernel<false, false, 1, true, 20>, dim3(((B + 19) / 20) * RU_CTAS), dim3(RU_THREADS), RU_SMEM_BYTES, st,
+            else if (pipe && nw20 && ((B + 19) / 20 <= m->rnn_umma_clusters || m->tune_rnn_clusters > 0))
+                // the batch fits the co-resident clusters with 20 windows each: smaller all-gather per step.  (rnn_clusters
+                // knob: fewer clusters, each walking several 20-window groups -- a narrower, longer kernel for laned runs)
+                launch_k(rnn_umma_kernel<false, false, 1, true, 20>,
+                    dim3((m->tune_rnn_clusters > 0 ? std::min((B + 19) / 20, std::min(m->tune_rnn_clusters, m->rnn_umma_clusters)) : (B + 19) / 20) * RU_CTAS),
+                    dim3(RU_THREADS), RU_SMEM_BYTES, st,
                     m->maps.w_hh.hi, m->maps.w_hh.lo, gi, reinterpret_cast<__half*>(hs), reinterpret_cast<__half*>(hs_lo),
                     m->blob + m->off.scales + SC_HH, B, L, g_rnn_tbuf, wh, wl);
             else if (pipe)
@@ -906,7 +915,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
             // that run as execution lanes, where its smaller footprint -- one CTA per row tile by default -- leaves SMs to the
             // other lanes' kernels; a lone forward is faster on the plain kernel's 148 CTAs), CTAs per launch, minimum row tiles.
             const int atm_mask = m->tune_atm >= 0 ? m->tune_atm : (m->laned ? 15 : 0);
-            const int atm_min_tiles = m->tune_atm_min_tiles, atm_grid = m->tune_atm_grid > 0 ? m->tune_atm_grid : TN;
+            const int atm_min_tiles = m->tune_atm_min_tiles, atm_grid = m->tune_atm_grid > 0 ? m->tune_atm_grid : (TN + 1) / 2;
             const int atm_bit = which == UG_IN ? 1 : which == UG_QKV ? 2 : which == UG_FF1 ? 4 : which == UG_IH ? 8 : 0;
             if (!ln && (atm_mask & atm_bit) && K == E && (N % AT_BN) == 0 && N <= AT_MAX_N_PER_UNIT && TN >= atm_min_tiles && !(dbg & 7)) {
                 const UmmaMaps& mp = m->maps;
@@ -921,6 +930,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
                 }
             }
             m->maps.ln_pair_min_k = m->tune_ln_pair;
+            m->maps.ln_grid = m->tune_ln_grid > 0 ? m->tune_ln_grid : (m->tune_ln_grid < 0 && m->laned ? (TN + 1) / 2 : 0);
             if (ln && TN <= skinny_tiles) {
                 Epi gp = ep;
                 gp.resid = gp.resid_lo = nullptr; gp.gamma = gp.beta = nullptr;

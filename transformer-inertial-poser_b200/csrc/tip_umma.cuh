@@ -851,6 +851,7 @@ struct UmmaMaps {
     UmmaOutput o_xa, o_xb, o_hid, o_qkv, o_gi;                             // TMA-store targets
     UmmaOperand w_hh;                                                      // resident A operand of the recurrence (box 64 x 64)
     int num_sms = 148;
+    int ln_grid = 0;                                                       // CTAs per fused-LayerNorm launch (0 = one per row tile)
     int ln_pair_min_k = 0;                                                 // LayerNorm GEMMs with K >= this run on CTA pairs (0 = never)
     bool attrs_set = false;
 };
@@ -1061,7 +1062,7 @@ inline void umma_gemm(UmmaMaps& mp, int which, int layer, int M, int N, int K, c
         else
             cudaLaunchKernelEx(&cfg, umma_gemm_kernel<256, true, true, 2>, A->hi, A->lo, mp.w_2h[layer].hi, mp.w_2h[layer].lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
     } else if (ln) {
-        const int tiles = m_tiles;                                // BN = 256 = the whole row
+        const int tiles = mp.ln_grid > 0 ? std::min(m_tiles, mp.ln_grid) : m_tiles;   // BN = 256 = the whole row; CTAs loop over the row tiles
         if (ep.drop_thr)
             launch_k(umma_gemm_kernel<256, true, true, 1, true>, dim3(std::min(tiles, mp.num_sms)), dim3(UM_THREADS), UmmaCfg<256>::SMEM_BYTES, st, A->hi, A->lo, B->hi, B->lo, c0, c1, Rm->hi, Rm->lo, M, N, K, m_tile0, m_tiles, ep);
         else
