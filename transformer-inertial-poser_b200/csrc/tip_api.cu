@@ -75,6 +75,7 @@ struct tip_model {
     bool laned = false;                 // this handle has lanes or is one: several forwards share the GPU (throughput mode)
     // tuning knobs (tip_set_tuning; initial values from the TIP_* environment)
     int tune_atm = -1;                  // GEMMs on the A-in-TMEM kernel: bit mask 1 in_linear, 2 qkv, 4 ff1, 8 rnn_ih; -1 = auto (all four when laned)
+    int tune_atm_pair = 0;              // ... on CTA pairs (cta_group::2: each CTA stages half of every W k-block)
     int tune_atm_grid = 0;              // CTAs per A-in-TMEM launch (0 = one per two 128-row tiles)
     int tune_atm_min_tiles = 64;        // ... for forwards of at least this many row tiles
     int tune_dyn_sched = 0;             // dynamic tile scheduler of the plain GEMMs
@@ -470,6 +471,7 @@ static void init_tuning(tip_model* m) {
     auto env = [](const char* k, int dflt) { const char* v = getenv(k); return v ? atoi(v) : dflt; };
     m->tune_atm = env("TIP_ATM", -1);
     m->tune_atm_grid = env("TIP_ATM_GRID", 0);
+    m->tune_atm_pair = env("TIP_ATM_PAIR", 0);
     m->tune_atm_min_tiles = env("TIP_ATM_MIN_TILES", 64);
     m->tune_dyn_sched = env("TIP_DYN_SCHED", 0);
     m->tune_ln_pair = env("TIP_LN_PAIR", 0);
@@ -481,6 +483,7 @@ extern "C" int tip_set_tuning(tip_model* m, const char* key, int value) {
     const std::string k(key);
     if (k == "atm") m->tune_atm = value;
     else if (k == "atm_grid") m->tune_atm_grid = value;
+    else if (k == "atm_pair") m->tune_atm_pair = value;
     else if (k == "atm_min_tiles") m->tune_atm_min_tiles = value;
     else if (k == "dyn_sched") m->tune_dyn_sched = value;
     else if (k == "ln_pair") m->tune_ln_pair = value;
@@ -924,6 +927,10 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
                 const UmmaOutput& Cm = which == UG_IN ? mp.o_xa : which == UG_QKV ? mp.o_qkv : which == UG_FF1 ? mp.o_hid : mp.o_gi;
                 if (Cm.valid) {
                     if (ep.tbuf) ep.tbuf = g_tbuf + 1024 + 64 * (which == UG_IN ? 0 : which == UG_QKV ? 1 : which == UG_FF1 ? 2 : 3);
+                    const UmmaOperand* B64 = which == UG_QKV ? &mp.w_qkv64[layer] : which == UG_FF1 ? &mp.w_164[layer] : which == UG_IH ? &mp.w_ih64 : nullptr;
+                    if (m->tune_atm_pair && B64 && (TN % 2) == 0 && (T0 % 2) == 0)
+                        launch_atm_pair_gemm(mp, Am, *B64, Cm, M, N, T0, TN, atm_grid, ep, st);
+                    else
                     launch_atm_gemm(mp, Am, Bm, Cm, M, N, T0, TN, atm_grid, ep, st);
                     m->launches++;
                     return;
