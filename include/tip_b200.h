@@ -214,6 +214,9 @@ int  tip_set_gemm_engine(tip_model* m, int engine);
  *   "ln_grid"       CTAs per fused-LayerNorm GEMM launch: 0 = one per 128-row tile, -1 (default) = that for a lone handle, one
  *                   per two row tiles on handles that are or own execution lanes (narrow kernels pack better across lanes)
  *   "rnn_clusters"  8-CTA clusters per tensor-core recurrence launch (0 = default: one per 20 windows)
+ *   "atm_pair"      1: the A-in-tensor-memory GEMMs run on CTA pairs (cta_group::2, each CTA stages half of W); default 0
+ *   "attn_grid"     attention: 0 (default) = one CTA per (window, 8 heads); N > 0 = N persistent CTAs with double-buffered
+ *                   K / V tiles; -1 = two such CTAs per SM
  * No reference counterpart (the reference has no kernels of its own). */
 int  tip_set_tuning(tip_model* m, const char* key, int value);
 /* CUDA-graph the forward for a fixed (B, L) (used by the streaming path); 0 disables. */

@@ -81,6 +81,7 @@ struct tip_model {
     int tune_dyn_sched = 0;             // dynamic tile scheduler of the plain GEMMs
     int tune_ln_pair = 0;               // LayerNorm GEMMs with K >= this on CTA pairs (0 = never)
     int tune_ln_grid = -1;              // CTAs per fused-LayerNorm GEMM launch (0 = one per 128-row tile; -1 = auto: one per two row tiles when laned)
+    int tune_attn_grid = 0;             // attention: 0 = one CTA per (window, 8 heads), one wave; N > 0 = N persistent double-buffered CTAs; -1 = two per SM
     int tune_rnn_clusters = 0;          // 8-CTA clusters per tensor-core recurrence launch (0 = as many as the batch needs / the GPU co-schedules)
     uint64_t pack_ordered_seq = 0;      // last pack this handle's streams are known to be ordered after (pack complete)
     uint64_t* d_seed = nullptr;         // base seed of the current stochastic call (device memory; graphs read it); followed by
@@ -477,6 +478,7 @@ static void init_tuning(tip_model* m) {
     m->tune_ln_pair = env("TIP_LN_PAIR", 0);
     m->tune_ln_grid = env("TIP_LN_GRID", -1);
     m->tune_rnn_clusters = env("TIP_RNN_UMMA_CLUSTERS", 0);
+    m->tune_attn_grid = env("TIP_ATTN_GRID", 0);
 }
 extern "C" int tip_set_tuning(tip_model* m, const char* key, int value) {
     if (!m || !key) return TIP_ERR_INVALID_ARG;
@@ -489,6 +491,7 @@ extern "C" int tip_set_tuning(tip_model* m, const char* key, int value) {
     else if (k == "ln_pair") m->tune_ln_pair = value;
     else if (k == "ln_grid") m->tune_ln_grid = value;
     else if (k == "rnn_clusters") m->tune_rnn_clusters = value;
+    else if (k == "attn_grid") m->tune_attn_grid = value;
     else { m->set_error("tip_set_tuning: unknown key '" + k + "'"); return TIP_ERR_INVALID_ARG; }
     drop_graphs(m);                     // captured forwards have the old kernel choice baked in
     return TIP_OK;
@@ -630,6 +633,16 @@ static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, fl
         const __half* ql = qh + (size_t)m->cap_rows * 3 * E;
         __half* oh = reinterpret_cast<__half*>(out) + (size_t)row0 * E;
         __half* ol = reinterpret_cast<__half*>(out_lo) + (size_t)row0 * E;
+        if (m->tune_attn_grid != 0 && hpb == 8) {
+            // persistent, double-buffered variant: tune_attn_grid CTAs (-1: two per SM) walk the (window, head group) units
+            static bool pipe_attr = false;
+            if (!pipe_attr) { cudaFuncSetAttribute(attention_mma_pipe_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * AttnCfg<8>::SMEM_BYTES); pipe_attr = true; }
+            const int units = B * (NH / 8);
+            const int grid = std::min(units, m->tune_attn_grid > 0 ? m->tune_attn_grid : 2 * m->maps.num_sms);
+            launch_k(attention_mma_pipe_kernel<8>, dim3(grid), dim3(256), 2 * AttnCfg<8>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, sp, seed, b0, B);
+            m->launches++;
+            return;
+        }
         // smaller CTAs (fewer heads each) quantise better over the SMs; the qkv pieces stay >= 64 bytes
         if (hpb == 8)      launch_k(attention_mma_kernel<8>, dim3(dim3(B, NH / 8)), dim3(256), AttnCfg<8>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, sp, seed, b0);
         else if (hpb == 2) launch_k(attention_mma_kernel<2>, dim3(dim3(B, NH / 2)), dim3(64), AttnCfg<2>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, sp, seed, b0);

@@ -209,4 +209,192 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
     }
 }
 
+// Persistent, software-pipelined variant: a CTA walks the (window, head group) units u = blockIdx.x, += gridDim.x with TWO
+// K / V tile sets in shared memory: the cp.async loads of the next unit are in flight while the current one is computed
+// and stored, so an SM no longer runs load -> compute -> store in lock-step for all its resident CTAs, and the launch can
+// be NARROW (a few CTAs per lane-share of the GPU) without losing per-SM efficiency.  Same arithmetic, same results.
+template <int AM_HPB>
+__global__ void __launch_bounds__(AM_HPB * 32, 2)
+attention_mma_pipe_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict__ qkv_lo,
+                          __half* __restrict__ out_hi, __half* __restrict__ out_lo, int L, float drop_p,
+                          const uint64_t* __restrict__ seed_ptr, uint64_t seed_off, int b0, int n_windows) {
+    constexpr int AM_ROWB = AttnCfg<AM_HPB>::ROWB, AM_QK_BYTES = AttnCfg<AM_HPB>::QK_BYTES, AM_V_BYTES = AttnCfg<AM_HPB>::V_BYTES;
+    constexpr int CPR = AM_HPB * 2;                  // 16-byte chunks per row of a plane tile
+    extern __shared__ __align__(16) uint8_t am_smem[];
+    griddep_wait();
+    griddep_launch();
+    constexpr int SET_BYTES = AttnCfg<AM_HPB>::SMEM_BYTES;        // one K / V tile set: [Kh | Kl | Vh | Vl]
+    constexpr int GROUPS = NH / AM_HPB;                           // head groups per window
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int units = n_windows * GROUPS;
+
+    // K, V rows of unit u -> tile set `base` with cp.async (16 B = 8 dims of one head)
+    auto issue_loads = [&](int u, uint8_t* base) {
+        const int ub = u / GROUPS, uh0 = (u - ub * GROUPS) * AM_HPB;
+        const size_t rb = (size_t)ub * L;
+        for (int i = tid; i < L * CPR * 4; i += AM_HPB * 32) {         // (row, {Kh,Kl,Vh,Vl}, chunk)
+            const int row = i / (4 * CPR), r = i - row * (4 * CPR), which = r / CPR, c = r - which * CPR;
+            const __half* src = ((which & 1) ? qkv_lo : qkv_hi) + (rb + row) * (3 * E) + (1 + (which >> 1)) * E + uh0 * HD + c * 8;
+            uint8_t* dst = base + (which == 0 ? 0 : which == 1 ? AM_QK_BYTES : which == 2 ? 2 * AM_QK_BYTES : 2 * AM_QK_BYTES + AM_V_BYTES)
+                           + row * AM_ROWB + c * 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        }
+    };
+    // V rows L..47 of both tile sets are zero for the whole launch (the loads only write rows < L; sO aliases the K planes)
+    for (int i = tid; i < 2 * (AM_VROWS - L) * CPR * 2; i += AM_HPB * 32) {
+        const int set = i / ((AM_VROWS - L) * CPR * 2), j = i - set * ((AM_VROWS - L) * CPR * 2);
+        const int plane = j & 1, c = (j >> 1) % CPR, row = L + (j >> 1) / CPR;
+        *reinterpret_cast<uint4*>(am_smem + set * SET_BYTES + 2 * AM_QK_BYTES + plane * AM_V_BYTES + row * AM_ROWB + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if ((int)blockIdx.x < units) issue_loads(blockIdx.x, am_smem);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    int iter = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++iter) {
+    uint8_t* sKh = am_smem + (iter & 1) * SET_BYTES;  // [L][8 heads][16] halves
+    uint8_t* sKl = sKh + AM_QK_BYTES;
+    uint8_t* sVh = sKl + AM_QK_BYTES;                // [48 keys][8 heads][16] halves, rows >= L zero
+    uint8_t* sVl = sVh + AM_V_BYTES;
+    float* sO = reinterpret_cast<float*>(sKh);       // [L][8 heads][16] fp32, aliases the K planes after they are consumed
+    const int b = u / GROUPS, h0 = (u - b * GROUPS) * AM_HPB;
+    const size_t rowbase = (size_t)b * L;
+    // the next unit's tiles -> the other set (free since the barrier that ended the previous iteration)
+    if (u + (int)gridDim.x < units) issue_loads(u + gridDim.x, am_smem + ((iter + 1) & 1) * SET_BYTES);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // ---- per warp: head hl ----
+    const int hl = warp;
+    // A fragments of Q (3 row tiles of 16) straight from the global planes; rows >= L are don't-care (clamped)
+    uint32_t qa_hi[3][4], qa_lo[3][4];
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt) {
+        const int r0 = min(16 * mt + g, L - 1), r1 = min(16 * mt + g + 8, L - 1);
+        const size_t o0 = (rowbase + r0) * (3 * E) + (h0 + hl) * HD + t4 * 2, o1 = (rowbase + r1) * (3 * E) + (h0 + hl) * HD + t4 * 2;
+        qa_hi[mt][0] = __ldg(reinterpret_cast<const uint32_t*>(qkv_hi + o0));     qa_lo[mt][0] = __ldg(reinterpret_cast<const uint32_t*>(qkv_lo + o0));
+        qa_hi[mt][1] = __ldg(reinterpret_cast<const uint32_t*>(qkv_hi + o1));     qa_lo[mt][1] = __ldg(reinterpret_cast<const uint32_t*>(qkv_lo + o1));
+        qa_hi[mt][2] = __ldg(reinterpret_cast<const uint32_t*>(qkv_hi + o0 + 8)); qa_lo[mt][2] = __ldg(reinterpret_cast<const uint32_t*>(qkv_lo + o0 + 8));
+        qa_hi[mt][3] = __ldg(reinterpret_cast<const uint32_t*>(qkv_hi + o1 + 8)); qa_lo[mt][3] = __ldg(reinterpret_cast<const uint32_t*>(qkv_lo + o1 + 8));
+    }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");      // this unit's tiles have landed (the next unit's may be in flight)
+    __syncthreads();
+    uint32_t kb_hi[5][2], kb_lo[5][2];               // B fragments of K^T (5 key tiles of 8)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt) {
+        const int o = (8 * nt + g) * AM_ROWB + hl * 32 + t4 * 4;
+        kb_hi[nt][0] = *reinterpret_cast<const uint32_t*>(sKh + o);      kb_lo[nt][0] = *reinterpret_cast<const uint32_t*>(sKl + o);
+        kb_hi[nt][1] = *reinterpret_cast<const uint32_t*>(sKh + o + 16); kb_lo[nt][1] = *reinterpret_cast<const uint32_t*>(sKl + o + 16);
+    }
+    __syncthreads();                                 // every warp holds its K fragments: the K planes may become sO
+
+    const float inv_keep = drop_inv_keep(drop_p);
+    const uint32_t dthr = drop_threshold(drop_p);
+    const uint64_t seed = drop_p > 0.f ? site_seed(seed_ptr, seed_off) : 0ull;
+    // ldmatrix.trans row addresses of this lane: lanes 0-7 -> keys +0..7, lanes 8-15 -> keys +8..15
+    const uint32_t vaddr_h = (uint32_t)__cvta_generic_to_shared(sVh) + (uint32_t)((lane & 15) * AM_ROWB + hl * 32);
+    const uint32_t vaddr_l = (uint32_t)__cvta_generic_to_shared(sVl) + (uint32_t)((lane & 15) * AM_ROWB + hl * 32);
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt) {
+        if (16 * mt >= L) break;                     // warp-uniform
+        const int ra = 16 * mt + g, rb = ra + 8;     // this lane's two query rows
+        // S tiles of the causal range: key tiles nt <= 2*mt + 1 (and < 5)
+        float s[6][4];
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            if (nt <= 2 * mt + 1 && nt < 5) {
+                mma_f16_16816(s[nt], qa_lo[mt], kb_hi[nt][0], kb_hi[nt][1]);
+                mma_f16_16816(s[nt], qa_hi[mt], kb_lo[nt][0], kb_lo[nt][1]);
+                mma_f16_16816(s[nt], qa_hi[mt], kb_hi[nt][0], kb_hi[nt][1]);
+            }
+        }
+        // mask (key <= query, key < L), un-scale (planes carry 16*q and 16*k), row max over the quad
+        // (key tiles beyond the causal range of this row tile are skipped at compile time: their probabilities are 0)
+        float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+            if (!(nt <= 2 * mt + 1 && nt < 5)) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int key = 8 * nt + 2 * t4 + e;
+                const bool live = key < L;
+                s[nt][e] = (live && key <= ra) ? s[nt][e] * (1.f / (ACT_SCALE * ACT_SCALE)) : -INFINITY;
+                s[nt][2 + e] = (live && key <= rb) ? s[nt][2 + e] * (1.f / (ACT_SCALE * ACT_SCALE)) : -INFINITY;
+                ma = fmaxf(ma, s[nt][e]);
+                mb = fmaxf(mb, s[nt][2 + e]);
+            }
+        }
+        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1)); ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+        // exp, row sums (fp32, before dropout), optional attention dropout (element index: attn_drop_index)
+        float la = 0.f, lb = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+            if (!(nt <= 2 * mt + 1 && nt < 5)) continue;         // s[nt] stays 0 there: contributes nothing to P V
+            float fa[2] = {1.f, 1.f}, fb[2] = {1.f, 1.f};
+            if (drop_p > 0.f) {
+                // this lane's four probabilities of the tile (rows ra, rb = ra + 8; keys key0, key0 + 1) = one hash group
+                const uint64_t grp = attn_drop_index((uint64_t)(b0 + b) * NH + h0 + hl, ra, 8 * nt + 2 * t4) >> 2;
+                const float4 f4 = dropout_factor4(seed, grp, dthr, inv_keep);
+                fa[0] = f4.x; fa[1] = f4.y; fb[0] = f4.z; fb[1] = f4.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float pa = exp2f((s[nt][e] - ma) * 1.4426950408889634f);        // exp(-inf) = 0 for masked slots
+                float pb = exp2f((s[nt][2 + e] - mb) * 1.4426950408889634f);
+                la += pa;
+                lb += pb;
+                s[nt][e] = pa * fa[e];
+                s[nt][2 + e] = pb * fb[e];
+            }
+        }
+        la += __shfl_xor_sync(0xffffffffu, la, 1); la += __shfl_xor_sync(0xffffffffu, la, 2);
+        lb += __shfl_xor_sync(0xffffffffu, lb, 1); lb += __shfl_xor_sync(0xffffffffu, lb, 2);
+        // O tile (16 x 16) = P V over the key steps ks <= mt (16 keys each)
+        float o[2][4];
+#pragma unroll
+        for (int dn = 0; dn < 2; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+            if (ks <= mt) {
+                uint32_t pa_hi[4], pa_lo[4];
+                split_pair(s[2 * ks][0], s[2 * ks][1], pa_hi[0], pa_lo[0]);
+                split_pair(s[2 * ks][2], s[2 * ks][3], pa_hi[1], pa_lo[1]);
+                split_pair(s[2 * ks + 1][0], s[2 * ks + 1][1], pa_hi[2], pa_lo[2]);
+                split_pair(s[2 * ks + 1][2], s[2 * ks + 1][3], pa_hi[3], pa_lo[3]);
+#pragma unroll
+                for (int dn = 0; dn < 2; ++dn) {
+                    // B fragment of V (k = 16 keys, n = 8 dims) straight from the row-major tile
+                    uint32_t vh0, vh1, vl0, vl1;
+                    const uint32_t off = (uint32_t)(16 * ks * AM_ROWB + dn * 16);
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(vh0), "=r"(vh1) : "r"(vaddr_h + off));
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(vl0), "=r"(vl1) : "r"(vaddr_l + off));
+                    mma_f16_16816(o[dn], pa_lo, vh0, vh1);
+                    mma_f16_16816(o[dn], pa_hi, vl0, vl1);
+                    mma_f16_16816(o[dn], pa_hi, vh0, vh1);
+                }
+            }
+        }
+        // o_true = acc / (16 * l); the output planes carry 16 * o_true = acc / l
+        const float ia = 1.f / la, ib = 1.f / lb;
+#pragma unroll
+        for (int dn = 0; dn < 2; ++dn) {
+            if (ra < L) *reinterpret_cast<float2*>(sO + ((size_t)ra * AM_HPB + hl) * HD + 8 * dn + 2 * t4) = make_float2(o[dn][0] * ia, o[dn][1] * ia);
+            if (rb < L) *reinterpret_cast<float2*>(sO + ((size_t)rb * AM_HPB + hl) * HD + 8 * dn + 2 * t4) = make_float2(o[dn][2] * ib, o[dn][3] * ib);
+        }
+    }
+    __syncthreads();
+    // ---- coalesced store: FP16 hi/lo planes of 16*o (the A operand of the out-projection GEMM) ----
+    __half* oh = out_hi + rowbase * E + h0 * HD;
+    __half* ol = out_lo + rowbase * E + h0 * HD;
+    for (int i = tid; i < L * (AM_HPB * HD / 4); i += AM_HPB * 32) {
+        const int row = i / (AM_HPB * HD / 4), c4 = i - row * (AM_HPB * HD / 4);
+        const float4 v = reinterpret_cast<const float4*>(sO + (size_t)row * AM_HPB * HD)[c4];
+        half_split_store4(oh + (size_t)row * E + c4 * 4, ol + (size_t)row * E + c4 * 4, v);
+    }
+    __syncthreads();                                 // sO (this tile set) is free for the loads of the unit after next
+    }
+}
+
+
 }  // namespace tip
