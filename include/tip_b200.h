@@ -207,12 +207,12 @@ int  tip_set_gemm_engine(tip_model* m, int engine);
  * fp32 round-off, every combination is parity-tested).  Keys:
  *   "atm"           GEMMs that run on the A-operand-in-tensor-memory kernel (csrc/tip_umma_atm.cuh): bit mask 1 in_linear,
  *                   2 qkv, 4 ff1, 8 rnn_ih; -1 (default) = all four on handles that are or own execution lanes, none otherwise
- *   "atm_grid"      CTAs per such launch (0 = one per two 128-row tiles)
+ *   "atm_grid"      CTAs per such launch (0 = one per two 128-row tiles, at most 40)
  *   "atm_min_tiles" ... used for forwards of at least this many 128-row tiles (default 64)
  *   "dyn_sched"     1: the plain GEMMs draw their tiles from a device counter instead of a static round-robin (default 0)
  *   "ln_pair"       LayerNorm GEMMs with K >= value run on CTA pairs (cta_group::2); 0 (default) = never
  *   "ln_grid"       CTAs per fused-LayerNorm GEMM launch: 0 = one per 128-row tile, -1 (default) = that for a lone handle, one
- *                   per two row tiles on handles that are or own execution lanes (narrow kernels pack better across lanes)
+ *                   per two row tiles (at most 40) on handles that are or own execution lanes (narrow kernels pack better across lanes)
  *   "rnn_clusters"  8-CTA clusters per tensor-core recurrence launch (0 = default: one per 20 windows)
  *   "atm_pair"      1: the A-in-tensor-memory GEMMs run on CTA pairs (cta_group::2, each CTA stages half of W); default 0
  *   "attn_grid"     attention: 0 (default) = one CTA per (window, 8 heads); N > 0 = N persistent CTAs with double-buffered

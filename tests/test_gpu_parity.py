@@ -664,3 +664,26 @@ def test_dynamic_scheduler_counters_rearm_across_launches_and_parts():
     y = m(xi[:150], xs[:150]).cpu().numpy()
     assert np.abs(y - want[:150]).max() < 2e-5
     assert torch.equal(m(xi, xs).cpu(), torch.from_numpy(want))
+
+
+def test_throughput_mode_batch_sizes():
+    """Handles that run as lanes choose the narrow throughput-mode kernels by themselves (A-in-TMEM GEMMs and LayerNorm GEMMs on
+    at most 40 CTAs from 64 row tiles on): bit-identical to a lone handle's full-width kernels at every batch size around
+    the switch points, including batches whose narrow launches give a CTA many row tiles (B = 1000: 313 tiles) and an odd
+    tile count (B = 205: 65 tiles)."""
+    from tip_b200.pipeline import ForwardLanes
+    sd = O.random_state_dict(37)
+    lone = make_model(sd)
+    owner = make_model(sd)
+    lanes = ForwardLanes(owner, 2)
+    for B in (200, 205, 256, 333, 1000):
+        x_imu, x_s = O.synth_inputs(700 + B, B, 40, nan_frac=0.02)
+        xi, xs = torch.from_numpy(x_imu).cuda(), torch.from_numpy(x_s).cuda()
+        want = lone(xi, xs)
+        lanes.fork()
+        ys = [lanes.forward(k, xi, xs) for k in range(2)]
+        lanes.join()
+        torch.cuda.synchronize()
+        for y in ys:
+            assert torch.equal(y, want), B
+    assert np.abs(want[:8].cpu().numpy() - O.forward(sd, x_imu[:8], x_s[:8])).max() < TOL

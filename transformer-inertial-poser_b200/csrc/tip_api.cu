@@ -66,6 +66,7 @@ static DropP drop_of(const tip_dropout* d) {
     return r;
 }
 
+constexpr int NARROW_CTAS = 40;                                          // width of a throughput-mode launch: about a quarter of the GPU (measured best at B = 256)
 constexpr int SCHED_SLOTS = 128;                                         // one per GEMM launch of a forward part (2 parts x 64)
 constexpr size_t SEED_SCHED_BYTES = sizeof(uint64_t) + SCHED_SLOTS * 2 * sizeof(int);
 
@@ -931,7 +932,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
             // that run as execution lanes, where its smaller footprint -- one CTA per row tile by default -- leaves SMs to the
             // other lanes' kernels; a lone forward is faster on the plain kernel's 148 CTAs), CTAs per launch, minimum row tiles.
             const int atm_mask = m->tune_atm >= 0 ? m->tune_atm : (m->laned ? 15 : 0);
-            const int atm_min_tiles = m->tune_atm_min_tiles, atm_grid = m->tune_atm_grid > 0 ? m->tune_atm_grid : (TN + 1) / 2;
+            const int atm_min_tiles = m->tune_atm_min_tiles, atm_grid = m->tune_atm_grid > 0 ? m->tune_atm_grid : std::min((TN + 1) / 2, NARROW_CTAS);
             const int atm_bit = which == UG_IN ? 1 : which == UG_QKV ? 2 : which == UG_FF1 ? 4 : which == UG_IH ? 8 : 0;
             if (!ln && (atm_mask & atm_bit) && K == E && (N % AT_BN) == 0 && N <= AT_MAX_N_PER_UNIT && TN >= atm_min_tiles && !(dbg & 7)) {
                 const UmmaMaps& mp = m->maps;
@@ -950,7 +951,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
                 }
             }
             m->maps.ln_pair_min_k = m->tune_ln_pair;
-            m->maps.ln_grid = m->tune_ln_grid > 0 ? m->tune_ln_grid : (m->tune_ln_grid < 0 && m->laned ? (TN + 1) / 2 : 0);
+            m->maps.ln_grid = m->tune_ln_grid > 0 ? m->tune_ln_grid : (m->tune_ln_grid < 0 && m->laned ? std::min((TN + 1) / 2, NARROW_CTAS) : 0);
             if (ln && TN <= skinny_tiles) {
                 Epi gp = ep;
                 gp.resid = gp.resid_lo = nullptr; gp.gamma = gp.beta = nullptr;
