@@ -2,21 +2,23 @@
 //
 // Why: with the 3-product FP16 split every k-step of a 128 x 128 tile reads 3 x (A 4 KB + B 4 KB) of operands from shared
 // memory -- 24 KB per 192 tensor-pipe clocks = the SM's whole 128 B/clk -- while TMA writes the next stages into the
-// same memory, and every 128 x 128 tile pulls 256 KB of operands through L2 (at 148 SMs that is the chip's L2 cap,
-// DESIGN 8).  For the wide GEMMs of the path (in_linear, qkv, ff1, rnn_ih: K = 256, N = 256 .. 1024) a work unit here is a
-// 128-row tile x a run of 128-column tiles:
-//   * the A tile (128 x 256, FP16 hi + lo = 128 KB) is loaded ONCE per unit -- TMA into the operand ring, then
+// same memory, and every 128 x 128 tile pulls 256 KB of operands plus 64 KB of output through the SM's port to L2, which
+// moves ~78 GB/s (loads and stores together; measured): that port is what paces the wide GEMMs of the path
+// (in_linear, qkv, ff1, rnn_ih: K = 256, N = 256 .. 1024).  Here
+//   * the A tile of a row tile (128 x 256, FP16 hi + lo = 128 KB) is loaded ONCE -- TMA into the operand ring, then
 //     `tcgen05.cp` (shared -> tensor memory, 128 lanes x 256 bit per instruction, the same swizzled K-major descriptors an
-//     SS MMA would read) into 256 columns of tensor memory -- and feeds `tcgen05.mma` with A in TMEM for all of the
-//     unit's n-tiles;
-//   * only W is streamed afterwards (TMA, 128B-swizzled 64-wide k-blocks, 4-stage ring): half the shared-memory reads
-//     per MMA and up to 44 % fewer operand bytes from L2.
+//     SS MMA would read) into 256 columns of tensor memory -- and feeds `tcgen05.mma` with A in TMEM (TS form) for every
+//     n-tile the CTA computes in that row tile;
+//   * only W is streamed afterwards (TMA, 128B-swizzled 64-wide k-blocks, 5-stage ring): half the shared-memory operand
+//     reads per MMA and up to 40 % fewer bytes through L2.  Same products in the same order as the plain kernel: the
+//     outputs are bit-identical.
 // Work split: the (row tile, n-tile) pairs of the GEMM in row-major order are cut into gridDim.x contiguous runs of
-// (nearly) equal length, one per CTA, so all SMs are busy although M / 128 is smaller than the SM count; a run that crosses
-// into the next row tile reloads A there (at most two A loads per CTA in the shapes of the path).
+// (nearly) equal length, one per CTA; a run that crosses into the next row tile reloads A there (1.8 us of latency, which
+// is why the kernel only ties the plain one on 148 CTAs).  Its use is the NARROW launch -- one CTA per two row tiles, each
+// A load amortised over all n-tiles -- of handles that run as execution lanes.
 // Accumulators: two 128-column TMEM buffers (the epilogue of n-tile i overlaps the MMAs of n-tile i + 1; an accumulator is
-// released as soon as it sits in registers).  Epilogue = bias / ReLU / dropout / FP16 hi-lo split or fp32, 32 x 32 boxes
-// through four rotating 2 KB shared tiles per warp, written by TMA stores.
+// released as soon as it sits in registers).  Epilogue = bias (slice fetched one tile ahead) / ReLU / dropout / FP16 hi-lo
+// split or fp32, 32 x 32 boxes through four rotating 2 KB shared tiles per warp, written by TMA stores.
 #pragma once
 #include "tip_umma.cuh"
 
