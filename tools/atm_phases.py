@@ -28,3 +28,7 @@ for k, name in enumerate(["in_linear", "qkv", "ff1", "rnn_ih"]):
     print("   tfull_seen   ", [r(12 + i) for i in range(8)])
     print("   acc_in_regs  ", [r(20 + i) for i in range(8)])
     print("   epi_done     ", [r(28 + i) for i in range(8)])
+t = [buf[1500 + i] for i in range(6)]
+if t[0]:
+    print("attention CTA 0 (us from start): loads issued + Q fragments requested", (t[1] - t[0]) / 1e3, "K/V landed", (t[2] - t[0]) / 1e3,
+          "K fragments in registers", (t[3] - t[0]) / 1e3, "S / softmax / PV done", (t[4] - t[0]) / 1e3, "stored", (t[5] - t[0]) / 1e3)

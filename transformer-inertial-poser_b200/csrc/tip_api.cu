@@ -645,9 +645,11 @@ static void launch_attention(tip_model* m, cudaStream_t st, const float* qkv, fl
             return;
         }
         // smaller CTAs (fewer heads each) quantise better over the SMs; the qkv pieces stay >= 64 bytes
-        if (hpb == 8)      launch_k(attention_mma_kernel<8>, dim3(dim3(B, NH / 8)), dim3(256), AttnCfg<8>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, sp, seed, b0);
-        else if (hpb == 2) launch_k(attention_mma_kernel<2>, dim3(dim3(B, NH / 2)), dim3(64), AttnCfg<2>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, sp, seed, b0);
-        else               launch_k(attention_mma_kernel<4>, dim3(dim3(B, NH / 4)), dim3(128), AttnCfg<4>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, sp, seed, b0);
+        static const int attn_ts = getenv("TIP_TS") ? atoi(getenv("TIP_TS")) : 0;
+        if (hpb == 8)      launch_k(attention_mma_kernel<8>, dim3(dim3(B, NH / 8)), dim3(256), AttnCfg<8>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, sp, seed, b0,
+                                    (attn_ts && g_tbuf) ? g_tbuf + 1500 : (unsigned long long*)nullptr);
+        else if (hpb == 2) launch_k(attention_mma_kernel<2>, dim3(dim3(B, NH / 2)), dim3(64), AttnCfg<2>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, sp, seed, b0, (unsigned long long*)nullptr);
+        else               launch_k(attention_mma_kernel<4>, dim3(dim3(B, NH / 4)), dim3(128), AttnCfg<4>::SMEM_BYTES, st, qh, ql, oh, ol, L, drop_p, sp, seed, b0, (unsigned long long*)nullptr);
         m->launches++;
         return;
     }

@@ -48,12 +48,14 @@ template <int AM_HPB>
 __global__ void __launch_bounds__(AM_HPB * 32, 1024 / (AM_HPB * 32) < 4 ? 1024 / (AM_HPB * 32) : 4)
 attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict__ qkv_lo,
                      __half* __restrict__ out_hi, __half* __restrict__ out_lo, int L, float drop_p,
-                     const uint64_t* __restrict__ seed_ptr, uint64_t seed_off, int b0) {
+                     const uint64_t* __restrict__ seed_ptr, uint64_t seed_off, int b0, unsigned long long* tbuf = nullptr) {
+#define AM_TS(i) do { if (tbuf && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tbuf[i] = t_; } } while (0)
     constexpr int AM_ROWB = AttnCfg<AM_HPB>::ROWB, AM_QK_BYTES = AttnCfg<AM_HPB>::QK_BYTES, AM_V_BYTES = AttnCfg<AM_HPB>::V_BYTES;
     constexpr int CPR = AM_HPB * 2;                  // 16-byte chunks per row of a plane tile
     extern __shared__ __align__(16) uint8_t am_smem[];
     griddep_wait();
     griddep_launch();
+    AM_TS(0);
     uint8_t* sKh = am_smem;                          // [L][8 heads][16] halves
     uint8_t* sKl = sKh + AM_QK_BYTES;
     uint8_t* sVh = sKl + AM_QK_BYTES;                // [48 keys][8 heads][16] halves, rows >= L zero
@@ -91,8 +93,10 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
         qa_hi[mt][2] = __ldg(reinterpret_cast<const uint32_t*>(qkv_hi + o0 + 8)); qa_lo[mt][2] = __ldg(reinterpret_cast<const uint32_t*>(qkv_lo + o0 + 8));
         qa_hi[mt][3] = __ldg(reinterpret_cast<const uint32_t*>(qkv_hi + o1 + 8)); qa_lo[mt][3] = __ldg(reinterpret_cast<const uint32_t*>(qkv_lo + o1 + 8));
     }
+    AM_TS(1);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    AM_TS(2);
     uint32_t kb_hi[5][2], kb_lo[5][2];               // B fragments of K^T (5 key tiles of 8)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt) {
@@ -101,6 +105,7 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
         kb_hi[nt][1] = *reinterpret_cast<const uint32_t*>(sKh + o + 16); kb_lo[nt][1] = *reinterpret_cast<const uint32_t*>(sKl + o + 16);
     }
     __syncthreads();                                 // every warp holds its K fragments: the K planes may become sO
+    AM_TS(3);
 
     const float inv_keep = drop_inv_keep(drop_p);
     const uint32_t dthr = drop_threshold(drop_p);
@@ -199,6 +204,7 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
         }
     }
     __syncthreads();
+    AM_TS(4);
     // ---- coalesced store: FP16 hi/lo planes of 16*o (the A operand of the out-projection GEMM) ----
     __half* oh = out_hi + rowbase * E + h0 * HD;
     __half* ol = out_lo + rowbase * E + h0 * HD;
@@ -207,6 +213,8 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
         const float4 v = reinterpret_cast<const float4*>(sO + (size_t)row * AM_HPB * HD)[c4];
         half_split_store4(oh + (size_t)row * E + c4 * 4, ol + (size_t)row * E + c4 * 4, v);
     }
+    AM_TS(5);
+#undef AM_TS
 }
 
 // Persistent, software-pipelined variant: a CTA walks the (window, head group) units u = blockIdx.x, += gridDim.x with TWO
