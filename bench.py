@@ -469,6 +469,8 @@ def main():
     # recurrence: 104 SMs) are filled by its neighbours' kernels.  Every step is still one full forward of one batch.
     from tip_b200.pipeline import ForwardLanes
     NL = args.lanes
+    if args.steps % NL and NL > 1:                      # keep the lanes evenly loaded: the K steps are dealt round-robin
+        NL = next((n for n in (NL - 1, NL + 1, NL - 2) if n >= 1 and args.steps % n == 0), NL)
     lanes = ForwardLanes(model, NL)
     outs = [torch.empty((B, L_WIN, 131), dtype=torch.float32, device=dev) for _ in range(NL)]
     if args.engine:
