@@ -947,7 +947,7 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
                     if (m->tune_atm_pair && B64 && (TN % 2) == 0 && (T0 % 2) == 0)
                         launch_atm_pair_gemm(mp, Am, *B64, Cm, M, N, T0, TN, atm_grid, ep, st);
                     else
-                    launch_atm_gemm(mp, Am, Bm, Cm, M, N, T0, TN, atm_grid, ep, st);
+                        launch_atm_gemm(mp, Am, Bm, Cm, M, N, T0, TN, atm_grid, ep, st);
                     m->launches++;
                     return;
                 }
