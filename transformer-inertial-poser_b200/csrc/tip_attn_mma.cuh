@@ -151,21 +151,29 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
 #pragma unroll
         for (int nt = 0; nt < 6; ++nt) {
             if (!(nt <= 2 * mt + 1 && nt < 5)) continue;         // s[nt] stays 0 there: contributes nothing to P V
-            float fa[2] = {1.f, 1.f}, fb[2] = {1.f, 1.f};
+            // this lane's four probabilities of the tile (rows ra, rb = ra + 8; keys key0, key0 + 1) = one hash group: lanes
+            // 0..3 of the hash = (ra, key0), (ra, key0 + 1), (rb, key0), (rb, key0 + 1).  A dropped probability becomes 0
+            // (one compare + select on the hash word, the 16-bit lane in the upper half); the kept ones' 1 / (1 - p) is
+            // applied once per row with the softmax normalisation below
+            uint32_t hl32 = 0xFFFFFFFFu, hh32 = 0xFFFFFFFFu;
             if (drop_p > 0.f) {
-                // this lane's four probabilities of the tile (rows ra, rb = ra + 8; keys key0, key0 + 1) = one hash group
                 const uint64_t grp = attn_drop_index((uint64_t)(b0 + b) * NH + h0 + hl, ra, 8 * nt + 2 * t4) >> 2;
-                const float4 f4 = dropout_factor4(seed, grp, dthr, inv_keep);
-                fa[0] = f4.x; fa[1] = f4.y; fb[0] = f4.z; fb[1] = f4.w;
+                const uint64_t hsh = hash_u64(seed, grp);
+                hl32 = (uint32_t)hsh; hh32 = (uint32_t)(hsh >> 32);
             }
+            const uint32_t thr_hi = dthr << 16;                          // (dthr <= 65535 whenever drop_p < 1)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 float pa = exp2f((s[nt][e] - ma) * 1.4426950408889634f);        // exp(-inf) = 0 for masked slots
                 float pb = exp2f((s[nt][2 + e] - mb) * 1.4426950408889634f);
                 la += pa;
                 lb += pb;
-                s[nt][e] = pa * fa[e];
-                s[nt][2 + e] = pb * fb[e];
+                if (drop_p > 0.f) {
+                    if ((e ? hl32 : (hl32 << 16)) < thr_hi) pa = 0.f;
+                    if ((e ? hh32 : (hh32 << 16)) < thr_hi) pb = 0.f;
+                }
+                s[nt][e] = pa;
+                s[nt][2 + e] = pb;
             }
         }
         la += __shfl_xor_sync(0xffffffffu, la, 1); la += __shfl_xor_sync(0xffffffffu, la, 2);
@@ -196,7 +204,7 @@ attention_mma_kernel(const __half* __restrict__ qkv_hi, const __half* __restrict
             }
         }
         // o_true = acc / (16 * l); the output planes carry 16 * o_true = acc / l
-        const float ia = 1.f / la, ib = 1.f / lb;
+        const float ia = inv_keep / la, ib = inv_keep / lb;
 #pragma unroll
         for (int dn = 0; dn < 2; ++dn) {
             if (ra < L) *reinterpret_cast<float2*>(sO + ((size_t)ra * AM_HPB + hl) * HD + 8 * dn + 2 * t4) = make_float2(o[dn][0] * ia, o[dn][1] * ia);
@@ -339,21 +347,29 @@ attention_mma_pipe_kernel(const __half* __restrict__ qkv_hi, const __half* __res
 #pragma unroll
         for (int nt = 0; nt < 6; ++nt) {
             if (!(nt <= 2 * mt + 1 && nt < 5)) continue;         // s[nt] stays 0 there: contributes nothing to P V
-            float fa[2] = {1.f, 1.f}, fb[2] = {1.f, 1.f};
+            // this lane's four probabilities of the tile (rows ra, rb = ra + 8; keys key0, key0 + 1) = one hash group: lanes
+            // 0..3 of the hash = (ra, key0), (ra, key0 + 1), (rb, key0), (rb, key0 + 1).  A dropped probability becomes 0
+            // (one compare + select on the hash word, the 16-bit lane in the upper half); the kept ones' 1 / (1 - p) is
+            // applied once per row with the softmax normalisation below
+            uint32_t hl32 = 0xFFFFFFFFu, hh32 = 0xFFFFFFFFu;
             if (drop_p > 0.f) {
-                // this lane's four probabilities of the tile (rows ra, rb = ra + 8; keys key0, key0 + 1) = one hash group
                 const uint64_t grp = attn_drop_index((uint64_t)(b0 + b) * NH + h0 + hl, ra, 8 * nt + 2 * t4) >> 2;
-                const float4 f4 = dropout_factor4(seed, grp, dthr, inv_keep);
-                fa[0] = f4.x; fa[1] = f4.y; fb[0] = f4.z; fb[1] = f4.w;
+                const uint64_t hsh = hash_u64(seed, grp);
+                hl32 = (uint32_t)hsh; hh32 = (uint32_t)(hsh >> 32);
             }
+            const uint32_t thr_hi = dthr << 16;                          // (dthr <= 65535 whenever drop_p < 1)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 float pa = exp2f((s[nt][e] - ma) * 1.4426950408889634f);        // exp(-inf) = 0 for masked slots
                 float pb = exp2f((s[nt][2 + e] - mb) * 1.4426950408889634f);
                 la += pa;
                 lb += pb;
-                s[nt][e] = pa * fa[e];
-                s[nt][2 + e] = pb * fb[e];
+                if (drop_p > 0.f) {
+                    if ((e ? hl32 : (hl32 << 16)) < thr_hi) pa = 0.f;
+                    if ((e ? hh32 : (hh32 << 16)) < thr_hi) pb = 0.f;
+                }
+                s[nt][e] = pa;
+                s[nt][2 + e] = pb;
             }
         }
         la += __shfl_xor_sync(0xffffffffu, la, 1); la += __shfl_xor_sync(0xffffffffu, la, 2);
@@ -384,7 +400,7 @@ attention_mma_pipe_kernel(const __half* __restrict__ qkv_hi, const __half* __res
             }
         }
         // o_true = acc / (16 * l); the output planes carry 16 * o_true = acc / l
-        const float ia = 1.f / la, ib = 1.f / lb;
+        const float ia = inv_keep / la, ib = inv_keep / lb;
 #pragma unroll
         for (int dn = 0; dn < 2; ++dn) {
             if (ra < L) *reinterpret_cast<float2*>(sO + ((size_t)ra * AM_HPB + hl) * HD + 8 * dn + 2 * t4) = make_float2(o[dn][0] * ia, o[dn][1] * ia);
