@@ -687,3 +687,8 @@ def test_throughput_mode_batch_sizes():
         for y in ys:
             assert torch.equal(y, want), B
     assert np.abs(want[:8].cpu().numpy() - O.forward(sd, x_imu[:8], x_s[:8])).max() < TOL
+    # the blocking host entry on a laned handle: its two batch parts (tile offset > 0 in the second) run the narrow kernels too
+    hi, hs = torch.from_numpy(x_imu).pin_memory(), torch.from_numpy(x_s).pin_memory()
+    for rep in range(3):
+        y = owner.forward_host(hi, hs)
+        assert float((y - want.cpu()).abs().max()) < 2e-5, rep
