@@ -386,6 +386,14 @@ def consumer_legs(frames=240):
     return out_rt, out_off
 
 
+def pick_lanes(steps, lanes):
+    """The K timed steps are dealt to the lanes round-robin; keep the lanes evenly loaded: when `lanes` does not divide K,
+    take the nearest count (lanes - 1, lanes + 1, lanes - 2) that does, else `lanes` itself."""
+    if lanes > 1 and steps % lanes:
+        return next((n for n in (lanes - 1, lanes + 1, lanes - 2) if n >= 1 and steps % n == 0), lanes)
+    return lanes
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -468,9 +476,7 @@ def main():
     # weights, own workspace) on their own streams, so one step's narrow phases (LayerNorm GEMMs: 80 row tiles,
     # recurrence: 104 SMs) are filled by its neighbours' kernels.  Every step is still one full forward of one batch.
     from tip_b200.pipeline import ForwardLanes
-    NL = args.lanes
-    if args.steps % NL and NL > 1:                      # keep the lanes evenly loaded: the K steps are dealt round-robin
-        NL = next((n for n in (NL - 1, NL + 1, NL - 2) if n >= 1 and args.steps % n == 0), NL)
+    NL = pick_lanes(args.steps, args.lanes)
     lanes = ForwardLanes(model, NL)
     outs = [torch.empty((B, L_WIN, 131), dtype=torch.float32, device=dev) for _ in range(NL)]
     if args.engine:

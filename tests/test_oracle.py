@@ -213,3 +213,15 @@ def test_bench_reference_arm_only_rank0_works_under_torchrun_env():
                         "--steps", "1", "--warmup", "1", "--batch", "8"], capture_output=True, text=True,
                        timeout=600, env=env)
     assert r.returncode == 0 and r.stdout.strip() == "", (r.stdout, r.stderr[-1000:])
+
+
+def test_bench_lane_count_follows_the_step_count():
+    """bench.py deals its K timed steps to the lanes round-robin: the lane count is adjusted so that it divides K."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.pick_lanes(20, 5) == 5 and b.pick_lanes(100, 5) == 5
+    assert b.pick_lanes(8, 5) == 4 and b.pick_lanes(12, 5) == 4 and b.pick_lanes(18, 5) == 6 and b.pick_lanes(9, 5) == 3
+    assert b.pick_lanes(7, 5) == 5 and b.pick_lanes(7, 1) == 1 and b.pick_lanes(1, 5) == 5
