@@ -699,6 +699,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                     }
                     ptx::mbar_wait(rfull_bar, (uint32_t)(it & 1));    // residual tile landed (issued right after the last k-block)
                     float rsum = 0.f;
+                    uint64_t sd_row = 0ull;                           // DROP: site seed + this row's first hash group (one shared-memory read per tile)
+                    if constexpr (DROP) sd_row = *seed_slot;
                     const uint8_t* rrow = smem + trow * 128;          // this row inside every 16 KB box
                     const int rsw = trow & 7;
 #pragma unroll
@@ -722,7 +724,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_const
                             uint32_t hw2[4] = {0u, 0u, 0u, 0u};
                             if constexpr (DROP) {
                                 const uint64_t g0 = ((uint64_t)(m0 + trow) * N + col0 + c * 32 + i * 8) >> 2;
-                                const uint64_t sd = *seed_slot;
+                                const uint64_t sd = sd_row;
                                 const uint64_t ha = hash_u64(sd, g0), hb2 = hash_u64(sd, g0 + 1);
                                 hw2[0] = (uint32_t)ha; hw2[1] = (uint32_t)(ha >> 32); hw2[2] = (uint32_t)hb2; hw2[3] = (uint32_t)(hb2 >> 32);
                             }
