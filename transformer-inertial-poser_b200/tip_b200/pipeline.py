@@ -11,8 +11,10 @@ before the previous result is needed -- offline evaluation, a serving loop over 
 * ``HostPipeline`` keeps several host-buffer jobs in flight through ``tip_forward_host_submit`` / ``_wait``
   (upload, forward and download of consecutive jobs overlap), optionally spread over lanes,
 
-both handing results back in submission order.  Windows stay independent; no arithmetic changes: every
-forward is the same whole-batch kernel sequence a blocking call runs.
+both handing results back in submission order.  Windows stay independent; no arithmetic changes: outputs are
+bit-identical to a blocking call's.  Handles that own or are lanes run in THROUGHPUT MODE (tip_set_tuning "auto"):
+their wide GEMMs and LayerNorm GEMMs are launched narrow (about a quarter of the GPU each), so that several
+lanes' kernels run side by side; 4-5 lanes is the measured sweet spot at B = 256 on a B200.
 """
 from __future__ import annotations
 
