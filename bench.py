@@ -521,6 +521,7 @@ def main():
     #  full-width ones, which is what a handle without lanes runs: select them for this leg)
     model.set_tuning("atm", 0)
     model.set_tuning("ln_grid", 0)
+    model.set_tuning("ln_share", 0)
     for i in range(2 if args.profile_run else 2 * n_sets):
         model(*sets[i % n_sets], out=outs[0])
     barrier()
@@ -540,6 +541,7 @@ def main():
         # legs (single_lane, the per-stage roofline pass) run the full-width kernels a handle without lanes uses
         model.set_tuning("atm", 0 if on else -1)
         model.set_tuning("ln_grid", 0 if on else -1)
+        model.set_tuning("ln_share", 0 if on else -1)
     lone_kernels(False)
 
     # ---- as shipped (the reference consumers' default: train mode, fresh Dropout(0.8) on the past state per call):
@@ -887,7 +889,8 @@ def main():
                    "lanes": NL, "cpus_bound_to_this_gpu": n_aff,
                    "throughput_mode": "handles that own / are lanes choose by themselves (tip_set_tuning auto): in_linear, qkv, ff1, "
                                       "rnn_ih on the A-operand-in-tensor-memory GEMM with one CTA per two 128-row tiles, fused "
-                                      "LayerNorm GEMMs with one CTA per two row tiles; same arithmetic, bit-identical outputs",
+                                      "LayerNorm GEMMs with one CTA per PAIR of row tiles sharing every W k-block; same arithmetic, "
+                                      "bit-identical outputs",
                    "engine": {0: "auto (tcgen05 3xFP16 split)", 1: "ffma", 2: "tcgen05-3xfp16"}[args.engine]},
         "timed_regions_ms": [round(r, 4) for r in regions],
         "timed_region_spread": (max(regions) - min(regions)) / dev_ms if dev_ms else None,

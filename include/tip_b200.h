@@ -213,6 +213,8 @@ int  tip_set_gemm_engine(tip_model* m, int engine);
  *   "ln_pair"       LayerNorm GEMMs with K >= value run on CTA pairs (cta_group::2); 0 (default) = never
  *   "ln_grid"       CTAs per fused-LayerNorm GEMM launch: 0 = one per 128-row tile, -1 (default) = that for a lone handle, one
  *                   per two row tiles (at most 40) on handles that are or own execution lanes (narrow kernels pack better across lanes)
+ *   "ln_share"      fused-LayerNorm GEMMs on the two-row-tile kernel (csrc/tip_umma_ln2.cuh: a CTA takes pairs of row tiles that
+ *                   share every W k-block): 1 on, 0 off, -1 (default) = on for handles that are or own execution lanes
  *   "rnn_clusters"  8-CTA clusters per tensor-core recurrence launch (0 = default: one per 20 windows)
  *   "atm_pair"      1: the A-in-tensor-memory GEMMs run on CTA pairs (cta_group::2, each CTA stages half of W); default 0
  *   "attn_grid"     attention: 0 (default) = one CTA per (window, 8 heads); N > 0 = N persistent CTAs with double-buffered

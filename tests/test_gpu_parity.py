@@ -600,7 +600,8 @@ def test_b256_released_checkpoint_golden():
 
 KNOBS = [dict(atm=15), dict(atm=15, atm_grid=148), dict(atm=15, atm_grid=37), dict(atm=5), dict(dyn_sched=1),
          dict(ln_pair=512), dict(atm=15, dyn_sched=1, ln_pair=512), dict(atm=15, atm_pair=1, atm_grid=80),
-         dict(atm=14, atm_pair=1, atm_grid=27, ln_grid=40), dict(attn_grid=80, ln_grid=27, rnn_clusters=5), dict(attn_grid=-1)]
+         dict(atm=14, atm_pair=1, atm_grid=27, ln_grid=40), dict(attn_grid=80, ln_grid=27, rnn_clusters=5), dict(attn_grid=-1),
+         dict(ln_share=1), dict(ln_share=1, ln_grid=7, atm=15), dict(ln_share=0, ln_grid=40)]
 
 
 @pytest.mark.parametrize("knobs", KNOBS, ids=["-".join(f"{k}{v}" for k, v in kn.items()) for kn in KNOBS])
@@ -610,7 +611,8 @@ def test_kernel_selection_knobs_match_reference_and_oracle(knobs):
     pairs over atm_grid CTAs: 80 = one row tile each, 148 = runs that cross row tiles, 37 = several row tiles per CTA),
     "dyn_sched" = the plain GEMMs draw tiles from a device counter, "ln_pair" = ff2 + LayerNorm on CTA pairs, "atm_pair" = the
     A-in-TMEM GEMMs on CTA pairs (cta_group::2 copies and MMAs), "ln_grid" / "attn_grid" / "rnn_clusters" = narrower
-    LayerNorm-GEMM / persistent double-buffered attention / recurrence launches.
+    LayerNorm-GEMM / persistent double-buffered attention / recurrence launches, "ln_share" = LayerNorm GEMMs whose CTAs take pairs
+    of row tiles sharing every W k-block (B = 205: the last pair holds a single tile).
     B = 256 (80 row tiles, the bench workload: golden from the reference module) and B = 205 (64.06 -> 65 row tiles: ragged
     last tile, odd tile count) in deterministic mode, B = 256 as shipped (dropout in the ff1 epilogue of the new kernel)
     mask for mask against the oracle; calls 2 and 3 of a shape are CUDA-graph capture and replay."""

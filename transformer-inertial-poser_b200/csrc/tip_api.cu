@@ -13,6 +13,7 @@
 #include "tip_qkv_attn.cuh"
 #include "tip_ffn_fused.cuh"
 #include "tip_umma_atm.cuh"
+#include "tip_umma_ln2.cuh"
 
 using namespace tip;
 
@@ -81,6 +82,7 @@ struct tip_model {
     int tune_atm_min_tiles = 64;        // ... for forwards of at least this many row tiles
     int tune_dyn_sched = 0;             // dynamic tile scheduler of the plain GEMMs
     int tune_ln_pair = 0;               // LayerNorm GEMMs with K >= this on CTA pairs (0 = never)
+    int tune_ln_share = -1;             // LayerNorm GEMMs on the two-row-tile kernel (W k-blocks shared): 1 on, 0 off, -1 auto (laned)
     int tune_ln_grid = -1;              // CTAs per fused-LayerNorm GEMM launch (0 = one per 128-row tile; -1 = auto: one per two row tiles when laned)
     int tune_attn_grid = 0;             // attention: 0 = one CTA per (window, 8 heads), one wave; N > 0 = N persistent double-buffered CTAs; -1 = two per SM
     int tune_rnn_clusters = 0;          // 8-CTA clusters per tensor-core recurrence launch (0 = as many as the batch needs / the GPU co-schedules)
@@ -478,6 +480,7 @@ static void init_tuning(tip_model* m) {
     m->tune_dyn_sched = env("TIP_DYN_SCHED", 0);
     m->tune_ln_pair = env("TIP_LN_PAIR", 0);
     m->tune_ln_grid = env("TIP_LN_GRID", -1);
+    m->tune_ln_share = env("TIP_LN_SHARE", -1);
     m->tune_rnn_clusters = env("TIP_RNN_UMMA_CLUSTERS", 0);
     m->tune_attn_grid = env("TIP_ATTN_GRID", 0);
 }
@@ -491,6 +494,7 @@ extern "C" int tip_set_tuning(tip_model* m, const char* key, int value) {
     else if (k == "dyn_sched") m->tune_dyn_sched = value;
     else if (k == "ln_pair") m->tune_ln_pair = value;
     else if (k == "ln_grid") m->tune_ln_grid = value;
+    else if (k == "ln_share") m->tune_ln_share = value;
     else if (k == "rnn_clusters") m->tune_rnn_clusters = value;
     else if (k == "attn_grid") m->tune_attn_grid = value;
     else { m->set_error("tip_set_tuning: unknown key '" + k + "'"); return TIP_ERR_INVALID_ARG; }
@@ -954,6 +958,15 @@ static int forward_chunk(tip_model* m, const float* x_imu, const float* x_s, flo
             }
             m->maps.ln_pair_min_k = m->tune_ln_pair;
             m->maps.ln_grid = m->tune_ln_grid > 0 ? m->tune_ln_grid : (m->tune_ln_grid < 0 && m->laned ? std::min((TN + 1) / 2, NARROW_CTAS) : 0);
+            // LayerNorm GEMMs in throughput mode: a CTA takes PAIRS of row tiles that share every W k-block (tip_umma_ln2.cuh).
+            // Knob "ln_share": 1 on, 0 off, -1 (default) = on for handles that run as lanes.
+            if (ln && TN > skinny_tiles && (which == UG_OUT || which == UG_FF2) && m->maps.o_xa.valid && m->maps.o_xb.valid &&
+                (m->tune_ln_share > 0 || (m->tune_ln_share < 0 && m->laned)) && !(dbg & 7) && !ts_on) {
+                const int cap = m->tune_ln_grid > 0 ? m->tune_ln_grid : NARROW_CTAS;
+                launch_ln2_gemm(m->maps, which, layer, M, N, K, T0, TN, cap, ep, st);
+                m->launches++;
+                return;
+            }
             if (ln && TN <= skinny_tiles) {
                 Epi gp = ep;
                 gp.resid = gp.resid_lo = nullptr; gp.gamma = gp.beta = nullptr;

@@ -842,6 +842,7 @@ struct UmmaMaps {
     UmmaOperand a_xin, a_xa, a_xb, a_att, a_hid, a_hs;                    // activations (box 32 x 128)
     UmmaOperand w_in, w_qkv[MAX_LAYERS], w_o[MAX_LAYERS], w_1[MAX_LAYERS], w_2[MAX_LAYERS], w_ih, w_l;
     UmmaOperand w_qkv256[MAX_LAYERS], w_1256[MAX_LAYERS], w_ih256;        // 256-row boxes of the same planes (wide tiles)
+    UmmaOperand a_att32, a_hid32, w_o32[MAX_LAYERS];                       // 32-column k-blocks of the LayerNorm GEMMs' operands (two-row-tile kernel, tip_umma_ln2.cuh; W2: w_2k32)
     UmmaOperand w_2h[MAX_LAYERS];                                          // W2, 128-row boxes: each CTA of a LayerNorm pair tile stages half of B
     UmmaOperand w_o64[MAX_LAYERS], w_264[MAX_LAYERS];                     // 64-row boxes (skinny-M LayerNorm GEMMs, 4 CTAs per row tile)
     UmmaOperand w_qkv64[MAX_LAYERS], w_164[MAX_LAYERS], w_ih64;           // 64-row boxes: each CTA of a 256 x 128 pair tile stages half of B
@@ -942,6 +943,8 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
     wgt(mp.w_l192k32, o.wl_hi, o.wl_lo, HEAD_NPAD, d.khead, 192, 32);      // rows 144..191 of the box: out of bounds -> zero fill
     act(mp.a_xb32, xb, plane_e, E, 32);
     act(mp.a_att, att, plane_e, E);
+    act(mp.a_att32, att, plane_e, E, 32);
+    act(mp.a_hid32, hid, plane_f, F, 32);
     act(mp.a_hid, hid, plane_f, F);
     act(mp.a_hs, hs, plane_r, R);
     wgt(mp.w_in, o.win_hi, o.win_lo, E, d.kin_pad, 128);
@@ -963,6 +966,7 @@ inline int umma_build_maps(UmmaMaps& mp, const float* blob, const PackOff& o, co
         wgt(mp.w_164[l], L.w1_hi, L.w1_lo, F, E, 64);
         wgt(mp.w_2[l], L.w2_hi, L.w2_lo, E, F, 256);
         wgt(mp.w_2h[l], L.w2_hi, L.w2_lo, E, F, 128);
+        wgt(mp.w_o32[l], L.wo_hi, L.wo_lo, E, E, 256, 32);
     }
     if (d.with_rnn) wgt(mp.w_ih, o.wih_hi, o.wih_lo, R, E, 128);
     if (d.with_rnn) wgt(mp.w_ih256, o.wih_hi, o.wih_lo, R, E, 256);

@@ -366,7 +366,7 @@ class TF_RNN_Past_State(nn.Module):
 
     def set_tuning(self, key: str, value: int):
         """Kernel-selection knob of the tcgen05 engine (tip_set_tuning): "atm", "atm_grid", "atm_min_tiles", "dyn_sched",
-        "ln_pair", "ln_grid", "rnn_clusters", "atm_pair", "attn_grid"; see include/tip_b200.h.  Per handle: lanes made by make_lane() have their own."""
+        "ln_pair", "ln_grid", "ln_share", "rnn_clusters", "atm_pair", "attn_grid"; see include/tip_b200.h.  Per handle: lanes made by make_lane() have their own."""
         dev = next(self.parameters()).device
         h = self._ensure(dev)
         capi.check(self._lib, h, self._lib.tip_set_tuning(h, key.encode(), int(value)), "tip_set_tuning")
