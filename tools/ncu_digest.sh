@@ -6,7 +6,7 @@ set -u
 tag=$1
 out=gpurun_out
 rep=/tmp/${tag}.ncu-rep
-N=1 ncu --set full --clock-control none --import-source on -k regex:"umma_gemm|umma_atm|attention_mma|rnn_umma|condition_kernel" -c 25 -o /tmp/${tag} python tools/one_forward.py > $out/${tag}_ncu.log 2>&1
+N=1 ncu --set full --clock-control none --import-source on -k regex:"umma_gemm|umma_atm|umma_ln2|attention_mma|rnn_umma|condition_kernel" -c 25 -o /tmp/${tag} python tools/one_forward.py > $out/${tag}_ncu.log 2>&1
 ncu -i $rep --page raw --csv > $out/${tag}_raw.csv 2>/dev/null
 python tools/ncu_summary.py $rep $out/${tag}_summary.csv $out/${tag}_traffic.json > /dev/null 2>&1
 : > $out/${tag}_stalls.txt
